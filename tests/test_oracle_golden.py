@@ -64,8 +64,9 @@ def test_restatement_filterbank(golden_constants, n_fft):
 
 
 def test_restatement_dct_and_window(golden_constants):
-    assert np.max(np.abs(restate.create_dct_ortho(40, 128) - golden_constants["dct"])) < 2e-7
-    assert np.max(np.abs(restate.hann_periodic(800) - golden_constants["hann800"])) < 1e-7
+    # torch evaluates both tables with float32 angles: its own tables sit ~1e-6 / 3e-7 off the exact formula
+    assert np.max(np.abs(restate.create_dct_ortho(40, 128) - golden_constants["dct"])) < 2e-6
+    assert np.max(np.abs(restate.hann_periodic(800) - golden_constants["hann800"])) < 5e-7
 
 
 @pytest.mark.parametrize("tag", ["nomask", "mask"])
@@ -99,7 +100,9 @@ def test_norm_oracle(golden_norm):
     for s in ("s0", "s1", "s2"):
         for k in ("mean", "std", "min", "max"):
             assert np.array_equal(st[s][k], g[f"{s}_{k}"]), (s, k)
-            assert np.max(np.abs(st64[s][k] - g[f"{s}_{k}"])) < 2e-5, (s, k)
+            # numpy reduces axis 0 of float32 rows sequentially: the reference's own statistics sit
+            # ~5e-5 off the exact value at this size; the fp64 restatement is the ground truth
+            assert np.max(np.abs(st64[s][k] - g[f"{s}_{k}"])) < 2e-4, (s, k)
     # windows: training-split utterance 2 (260 frames -> 2 windows), short utterance 0 (padded)
     for u in (0, 2, 5):
         for i, w in enumerate(onorm.windows_of(feats[u])):
