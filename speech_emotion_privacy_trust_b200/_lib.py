@@ -1,0 +1,74 @@
+"""ctypes binding of libsept_b200.so (include/sept.h).  There is no CPU fallback: a missing library is built with
+nvcc if the toolchain is present, otherwise importing the compute layer fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import build as _build
+
+_LIB = None
+
+c_f32p = C.c_void_p      # device / host pointers travel as integers (tensor.data_ptr())
+c_ptr = C.c_void_p
+
+_SIGNATURES = {
+    "sept_version": (C.c_int, []),
+    "sept_last_error": (C.c_char_p, []),
+    "sept_init": (C.c_int, [C.c_int]),
+    "sept_frames_per_item": (C.c_int, [C.c_int]),
+    "sept_extract_layout": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "sept_logmel_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "sept_mfcc_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "sept_speaker_stats_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "sept_normalize_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "sept_normalize_windows_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "sept_cloak_fwd_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float,
+                                     C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "sept_cloak_bwd_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "sept_cloak_grl_bwd_f32": (C.c_int, [c_ptr, c_ptr, C.c_float, c_ptr, c_ptr, c_ptr, C.c_float, C.c_float, C.c_int, C.c_int,
+                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "sept_grl_bwd_f32": (C.c_int, [c_ptr, C.c_float, C.c_int64, c_ptr, c_ptr]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+SEPT_E_BADARG, SEPT_E_UNSUPPORTED, SEPT_E_TOO_SHORT, SEPT_E_CUDA = -1, -2, -3, -4
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the .so is absent or stale and nvcc exists).  Raises if neither is possible."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        try:
+            path = _build.build()
+        except RuntimeError:
+            if not path.exists():
+                raise
+        handle = C.CDLL(str(path))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = handle
+    return _LIB
+
+
+def check(rc: int) -> None:
+    """Map a status code to the exception the reference's Python would have raised."""
+    if rc == 0:
+        return
+    msg = lib().sept_last_error().decode()
+    if rc in (SEPT_E_BADARG, SEPT_E_UNSUPPORTED):
+        raise ValueError(msg)
+    raise RuntimeError(msg)       # too-short utterance (torch.stft raises RuntimeError too) and CUDA errors
+
+
+def require_cuda(t) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("speech_emotion_privacy_trust_b200 computes on a CUDA device only (no CPU fallback); "
+                           f"got a tensor on {t.device}")

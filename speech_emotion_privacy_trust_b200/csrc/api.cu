@@ -1,0 +1,309 @@
+// C ABI of libsept_b200 (include/sept.h): argument checking, the per-device constant cache, kernel launches.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/sept.h"
+#include "cloak.h"
+#include "extract.h"
+#include "norm.h"
+#include "tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(SEPT_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define SEPT_CUDA(call)                                                  \
+    do {                                                                 \
+        cudaError_t e_ = (call);                                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);              \
+    } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- immutable per-(device, n_fft, n_mels) constants -------------------------------------------------------------
+struct ExtractConsts {
+    float* window = nullptr;
+    float* tws = nullptr;
+    void* taps = nullptr;
+    int32_t* band_ptr = nullptr;
+    int n_taps = 0;
+};
+
+std::mutex g_mu;
+std::map<std::tuple<int, int, int>, ExtractConsts> g_consts;
+std::map<int, float*> g_dct;
+std::map<int, int> g_sm_count;
+
+template <class T>
+cudaError_t upload(const std::vector<T>& h, T** d) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(d), h.size() * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+int get_consts(int n_fft, int n_mels, ExtractConsts* out, int* sm_count) {
+    int dev = 0;
+    SEPT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_sm_count.count(dev)) {
+        int n = 0;
+        SEPT_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        g_sm_count[dev] = n;
+    }
+    *sm_count = g_sm_count[dev];
+    auto key = std::make_tuple(dev, n_fft, n_mels);
+    auto it = g_consts.find(key);
+    if (it == g_consts.end()) {
+        ExtractConsts c;
+        std::vector<float> win = sept::make_hann_periodic(n_fft);
+        std::vector<float> tws = sept::make_split_twiddles(n_fft);
+        std::vector<int32_t> bp;
+        std::vector<sept::MelTap> taps;
+        sept::make_mel_taps(n_fft, n_mels, 16000, bp, taps);
+        c.n_taps = (int)taps.size();
+        sept::MelTap* dtaps = nullptr;
+        SEPT_CUDA(upload(win, &c.window));
+        SEPT_CUDA(upload(tws, &c.tws));
+        SEPT_CUDA(upload(taps, &dtaps));
+        SEPT_CUDA(upload(bp, &c.band_ptr));
+        c.taps = dtaps;
+        it = g_consts.emplace(key, c).first;
+    }
+    *out = it->second;
+    return SEPT_OK;
+}
+
+int get_dct(float** out) {
+    int dev = 0;
+    SEPT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_dct.find(dev);
+    if (it == g_dct.end()) {
+        std::vector<float> d = sept::make_dct_ortho(40, 128);
+        float* dd = nullptr;
+        SEPT_CUDA(upload(d, &dd));
+        it = g_dct.emplace(dev, dd).first;
+    }
+    *out = it->second;
+    return SEPT_OK;
+}
+
+bool supported_n_fft(int n_fft) { return n_fft == 400 || n_fft == 800 || n_fft == 1600; }
+
+int check_extract_shape(int n_fft, int hop, int n_mels, int n_taps) {
+    if (!supported_n_fft(n_fft))
+        return fail(SEPT_E_UNSUPPORTED, "n_fft=%d unsupported: the kernels cover 400, 800 and 1600 (2^a * 25)", n_fft);
+    if (hop <= 0 || (hop & 1) || hop > n_fft)
+        return fail(SEPT_E_UNSUPPORTED, "hop=%d unsupported: must be even and in (0, n_fft]", hop);
+    if (n_mels <= 0 || n_mels > 512) return fail(SEPT_E_UNSUPPORTED, "n_mels=%d unsupported (1..512)", n_mels);
+    if (n_taps >= 0 && sept::extract_smem_bytes_for(n_fft, hop, n_taps, n_mels) > 227 * 1024)
+        return fail(SEPT_E_UNSUPPORTED, "n_fft=%d hop=%d n_mels=%d does not fit the 227 KB of shared memory", n_fft, hop,
+                    n_mels);
+    return SEPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sept_version(void) { return 100; }
+
+const char* sept_last_error(void) { return g_err.c_str(); }
+
+int sept_init(int n_mels) {
+    for (int n_fft : {400, 800, 1600}) {
+        ExtractConsts c;
+        int sms;
+        int rc = get_consts(n_fft, n_mels, &c, &sms);
+        if (rc) return rc;
+    }
+    float* d;
+    return get_dct(&d);
+}
+
+int sept_frames_per_item(int n_fft) { return sept::extract_frames_per_item(n_fft); }
+
+int sept_extract_layout(const int64_t* utt_off, int n_utts, int n_fft, int hop, int64_t* frame_off, int32_t* item_off) {
+    if (!utt_off || !frame_off || !item_off || n_utts < 0) return fail(SEPT_E_BADARG, "sept_extract_layout: bad argument");
+    int rc = check_extract_shape(n_fft, hop, 1, -1);
+    if (rc) return rc;
+    const int fpw = sept::extract_frames_per_item(n_fft);
+    frame_off[0] = 0;
+    item_off[0] = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        const int64_t n = utt_off[u + 1] - utt_off[u];
+        if (n <= n_fft / 2)
+            return fail(SEPT_E_TOO_SHORT, "utterance %d has %lld samples; reflect padding of %d needs more", u, (long long)n,
+                        n_fft / 2);
+        if (n >= (int64_t)1 << 31) return fail(SEPT_E_BADARG, "utterance %d is longer than 2^31 samples", u);
+        const int64_t T = 1 + n / hop;
+        frame_off[u + 1] = frame_off[u] + T;
+        const int64_t items = item_off[u] + (T + fpw - 1) / fpw;
+        if (items >= (int64_t)1 << 31) return fail(SEPT_E_BADARG, "batch exceeds 2^31 work items; split it");
+        item_off[u + 1] = (int32_t)items;
+    }
+    return SEPT_OK;
+}
+
+int sept_logmel_f32(const float* wav, const int64_t* utt_off, const int64_t* frame_off, const int32_t* item_off,
+                    int n_utts, int n_fft, int hop, int n_mels, int deriv, int layout, float* out, sept_stream_t stream) {
+    if (n_utts == 0) return SEPT_OK;
+    if (!wav || !utt_off || !frame_off || !item_off || !out || n_utts < 0)
+        return fail(SEPT_E_BADARG, "sept_logmel_f32: null pointer or negative n_utts");
+    if (layout != SEPT_LAYOUT_FRAME_MAJOR && layout != SEPT_LAYOUT_BAND_MAJOR)
+        return fail(SEPT_E_BADARG, "sept_logmel_f32: layout %d", layout);
+    int rc = check_extract_shape(n_fft, hop, n_mels, -1);
+    if (rc) return rc;
+    ExtractConsts c;
+    int sms = 0;
+    rc = get_consts(n_fft, n_mels, &c, &sms);
+    if (rc) return rc;
+    rc = check_extract_shape(n_fft, hop, n_mels, c.n_taps);
+    if (rc) return rc;
+    sept::ExtractParams p{};
+    p.wav = wav; p.utt_off = utt_off; p.frame_off = frame_off; p.item_off = item_off;
+    p.n_utts = n_utts; p.hop = hop; p.n_mels = n_mels; p.n_taps = c.n_taps; p.deriv = deriv ? 1 : 0;
+    p.window = c.window; p.tws = c.tws; p.taps = c.taps; p.band_ptr = c.band_ptr;
+    p.out = out;
+    const int mode = layout == SEPT_LAYOUT_FRAME_MAJOR ? sept::kModeDbFrameMajor : sept::kModeDbBandMajor;
+    SEPT_CUDA(sept::launch_extract(p, n_fft, mode, sms, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+int sept_mfcc_f32(const float* wav, const int64_t* utt_off, const int64_t* frame_off, const int32_t* item_off, int n_utts,
+                  int64_t total_frames, float* scratch, int32_t* utt_max, float* out, sept_stream_t stream) {
+    if (n_utts == 0) return SEPT_OK;
+    if (!wav || !utt_off || !frame_off || !item_off || !scratch || !utt_max || !out || n_utts < 0 || total_frames <= 0)
+        return fail(SEPT_E_BADARG, "sept_mfcc_f32: null pointer or bad size");
+    ExtractConsts c;
+    int sms = 0;
+    int rc = get_consts(400, 128, &c, &sms);
+    if (rc) return rc;
+    float* dct = nullptr;
+    rc = get_dct(&dct);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SEPT_CUDA(cudaMemsetAsync(utt_max, 0, sizeof(int32_t) * 2 * (size_t)n_utts, st));
+    sept::ExtractParams p{};
+    p.wav = wav; p.utt_off = utt_off; p.frame_off = frame_off; p.item_off = item_off;
+    p.n_utts = n_utts; p.hop = 200; p.n_mels = 128; p.n_taps = c.n_taps; p.total_frames = total_frames;
+    p.window = c.window; p.tws = c.tws; p.taps = c.taps; p.band_ptr = c.band_ptr;
+    p.out = scratch; p.utt_max = utt_max;
+    SEPT_CUDA(sept::launch_extract(p, 400, sept::kModeMfccPower, sms, st));
+    sept::MfccDctParams d{};
+    d.power = scratch; d.utt_max = utt_max; d.frame_off = frame_off; d.dct = dct; d.n_utts = n_utts;
+    d.total_frames = total_frames; d.top_db = 80.0f; d.out = out;
+    SEPT_CUDA(sept::launch_mfcc_dct(d, st));
+    return SEPT_OK;
+}
+
+int sept_speaker_stats_f32(const float* feat, const int64_t* frame_off, const uint8_t* whole, int n_utts, int n_feat,
+                           int win_len, int shift_len, const int32_t* spk_ptr, const int32_t* spk_utts, int n_spk,
+                           float* utt_partial, float* stats, sept_stream_t stream) {
+    if (!feat || !frame_off || !spk_ptr || !spk_utts || !utt_partial || !stats || n_utts < 0 || n_spk < 0 || n_feat <= 0 ||
+        win_len <= 0 || shift_len <= 0)
+        return fail(SEPT_E_BADARG, "sept_speaker_stats_f32: bad argument");
+    sept::SpeakerStatsParams p{};
+    p.feat = feat; p.frame_off = frame_off; p.whole = whole; p.n_utts = n_utts; p.n_feat = n_feat;
+    p.win_len = win_len; p.shift_len = shift_len; p.utt_partial = utt_partial; p.spk_ptr = spk_ptr;
+    p.spk_utts = spk_utts; p.n_spk = n_spk; p.stats = stats;
+    SEPT_CUDA(sept::launch_speaker_stats(p, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+int sept_normalize_f32(const float* feat, const int64_t* frame_off, const int32_t* spk_of_utt, const float* stats,
+                       int n_utts, int n_feat, int mode, float* out, sept_stream_t stream) {
+    if (!feat || !frame_off || !spk_of_utt || !stats || !out || n_utts < 0 || n_feat <= 0 ||
+        (mode != SEPT_NORM_ZNORM && mode != SEPT_NORM_MINMAX))
+        return fail(SEPT_E_BADARG, "sept_normalize_f32: bad argument");
+    sept::NormalizeParams p{};
+    p.feat = feat; p.frame_off = frame_off; p.spk_of_utt = spk_of_utt; p.stats = stats; p.n_feat = n_feat;
+    p.mode = mode; p.n_utts = n_utts; p.out = out;
+    SEPT_CUDA(sept::launch_normalize(p, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+int sept_normalize_windows_f32(const float* feat, const int64_t* frame_off, const int32_t* spk_of_utt,
+                               const float* stats, const int32_t* win_utt, const int32_t* win_t0, int n_windows,
+                               int win_len, int n_feat, int mode, float* out, sept_stream_t stream) {
+    if (!feat || !frame_off || !spk_of_utt || !stats || !win_utt || !win_t0 || !out || n_windows < 0 || win_len <= 0 ||
+        n_feat <= 0 || (mode != SEPT_NORM_ZNORM && mode != SEPT_NORM_MINMAX))
+        return fail(SEPT_E_BADARG, "sept_normalize_windows_f32: bad argument");
+    sept::NormalizeParams p{};
+    p.feat = feat; p.frame_off = frame_off; p.spk_of_utt = spk_of_utt; p.stats = stats; p.n_feat = n_feat;
+    p.mode = mode; p.win_utt = win_utt; p.win_t0 = win_t0; p.n_windows = n_windows; p.win_len = win_len; p.out = out;
+    SEPT_CUDA(sept::launch_normalize(p, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+int sept_cloak_fwd_f32(const float* x, const float* locs, const float* rhos, const float* mask, const float* eps,
+                       uint64_t seed, uint64_t offset, float eps_std, float min_scale, float max_scale, int batch, int wf,
+                       float* out, float* eps_out, float* noise_out, sept_stream_t stream) {
+    if (!x || !locs || !rhos || !out || batch < 0 || wf <= 0) return fail(SEPT_E_BADARG, "sept_cloak_fwd_f32: bad argument");
+    if (wf % 4) return fail(SEPT_E_BADARG, "sept_cloak_fwd_f32: W*F=%d must be a multiple of 4", wf);
+    if (!aligned16(x) || !aligned16(locs) || !aligned16(rhos) || !aligned16(mask) || !aligned16(eps) || !aligned16(out) ||
+        !aligned16(eps_out) || !aligned16(noise_out))
+        return fail(SEPT_E_BADARG, "sept_cloak_fwd_f32: pointers must be 16-byte aligned");
+    sept::CloakFwdParams p{};
+    p.x = x; p.locs = locs; p.rhos = rhos; p.mask = mask; p.eps = eps; p.seed = seed; p.offset = offset;
+    p.eps_std = eps_std; p.min_scale = min_scale; p.max_scale = max_scale; p.batch = batch; p.wf = wf; p.out = out;
+    p.eps_out = eps_out; p.noise_out = noise_out;
+    SEPT_CUDA(sept::launch_cloak_fwd(p, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+size_t sept_cloak_bwd_workspace_bytes(int wf) {
+    if (wf <= 0) return 0;
+    return (size_t)sept::kCloakSlices * wf * sizeof(float) + ((size_t)(wf + 511) / 512) * sizeof(unsigned) + 16;
+}
+
+int sept_cloak_grl_bwd_f32(const float* g_a, const float* g_b, float lambda, const float* eps, const float* rhos,
+                           const float* mask, float min_scale, float max_scale, int batch, int wf, void* workspace,
+                           float* dlocs, float* drhos, float* dx, sept_stream_t stream) {
+    if (!g_a || !eps || !rhos || !workspace || !dlocs || batch < 0 || wf <= 0)
+        return fail(SEPT_E_BADARG, "sept_cloak_grl_bwd_f32: bad argument");
+    if (wf % 4) return fail(SEPT_E_BADARG, "sept_cloak_grl_bwd_f32: W*F=%d must be a multiple of 4", wf);
+    if (!aligned16(g_a) || !aligned16(g_b) || !aligned16(eps) || !aligned16(rhos) || !aligned16(mask) ||
+        !aligned16(workspace) || !aligned16(dlocs) || !aligned16(drhos) || !aligned16(dx))
+        return fail(SEPT_E_BADARG, "sept_cloak_grl_bwd_f32: pointers must be 16-byte aligned");
+    sept::CloakBwdParams p{};
+    p.g_a = g_a; p.g_b = g_b; p.lambda = lambda; p.eps = eps; p.rhos = rhos; p.mask = mask;
+    p.min_scale = min_scale; p.max_scale = max_scale; p.reg_coef = 0.f; p.batch = batch; p.wf = wf;
+    p.partial = static_cast<float*>(workspace);
+    p.counters = reinterpret_cast<unsigned*>(static_cast<float*>(workspace) + (size_t)sept::kCloakSlices * wf);
+    p.dlocs = dlocs; p.drhos = drhos; p.dx = dx;
+    SEPT_CUDA(sept::launch_cloak_bwd(p, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+int sept_grl_bwd_f32(const float* g, float lambda, int64_t n, float* dx, sept_stream_t stream) {
+    if (n == 0) return SEPT_OK;
+    if (!g || !dx || n < 0) return fail(SEPT_E_BADARG, "sept_grl_bwd_f32: bad argument");
+    if (!aligned16(g) || !aligned16(dx)) return fail(SEPT_E_BADARG, "sept_grl_bwd_f32: pointers must be 16-byte aligned");
+    SEPT_CUDA(sept::launch_grl_bwd(g, lambda, (size_t)n, dx, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+}  // extern "C"

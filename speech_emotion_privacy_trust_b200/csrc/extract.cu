@@ -1,0 +1,264 @@
+// Fused speech feature extraction kernels for sm_100a (see extract_core.cuh for the per-lane phases).
+//
+//   extract_kernel<R, MODE>   persistent, one CTA per SM; each WARP walks its share of the items (an item = FPW
+//                             consecutive frames of one utterance) through stage -> window+DFT25 -> DFT-R ->
+//                             real split+power -> sparse mel -> log, touching HBM only for the waveform span
+//                             and the finished features.
+//   mfcc_dct_kernel           second phase of MFCC: per-utterance top_db floor + ortho DCT-II.
+//
+// Replaces torchaudio MelSpectrogram/AmplitudeToDB/MFCC as called by
+// feature_extraction/audio_feature_extraction.py:15-46 of the reference.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "extract.h"
+#include "extract_core.cuh"
+
+namespace sept {
+
+constexpr float kDbPerLog2 = 3.01029995663981195f;   // 10*log10(2)
+constexpr float kAmin = 1e-10f;                        // amplitude_to_DB amin (functional.py:390)
+
+__device__ __forceinline__ float power_to_db(float p) { return kDbPerLog2 * __log2f(fmaxf(p, kAmin)); }
+
+// first utterance u with item_off[u+1] > item
+__device__ __forceinline__ int find_utt(const int32_t* __restrict__ item_off, int n_utts, int item) {
+    int lo_ = 0, hi_ = n_utts - 1;
+    while (lo_ < hi_) {
+        const int mid = (lo_ + hi_) >> 1;
+        if (__ldg(item_off + mid + 1) > item) hi_ = mid; else lo_ = mid + 1;
+    }
+    return lo_;
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel(const ExtractParams prm) {
+    using G = Geo<R>;
+    constexpr int kExtractWarps = ExtractWarps<R>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hop = prm.hop, n_mels = prm.n_mels;
+    const int span4 = (G::span(hop) + 3) & ~3;
+
+    // ---- CTA-shared constants -----------------------------------------------------------------------------
+    f4* tws = reinterpret_cast<f4*>(smem_raw);                                   // [13][R]
+    f2* win2 = reinterpret_cast<f2*>(tws + 13 * R);                              // [NC]
+    tap_t* taps = reinterpret_cast<tap_t*>(win2 + G::NC);                        // [n_taps]
+    int* band_ptr = reinterpret_cast<int*>(taps + prm.n_taps);                   // [n_mels + 1]
+    const int const_bytes = (13 * R * 16 + G::NC * 8 + prm.n_taps * 8 + (n_mels + 1) * 4 + 15) & ~15;
+    for (int i = threadIdx.x; i < 13 * R; i += blockDim.x) tws[i] = reinterpret_cast<const f4*>(prm.tws)[i];
+    for (int i = threadIdx.x; i < G::NC; i += blockDim.x) win2[i] = reinterpret_cast<const f2*>(prm.window)[i];
+    for (int i = threadIdx.x; i < prm.n_taps; i += blockDim.x) taps[i] = reinterpret_cast<const tap_t*>(prm.taps)[i];
+    for (int i = threadIdx.x; i <= n_mels; i += blockDim.x) band_ptr[i] = prm.band_ptr[i];
+    __syncthreads();
+
+    // ---- warp-private tiles -------------------------------------------------------------------------------
+    const int warp_bytes = span4 * 4 + G::Y_PK4 * 16;
+    unsigned char* wbase = smem_raw + const_bytes + warp * warp_bytes;
+    float* stage = reinterpret_cast<float*>(wbase);
+    pk4* Y = reinterpret_cast<pk4*>(wbase + span4 * 4);
+    pk2* P = reinterpret_cast<pk2*>(Y);
+
+    // ---- this CTA's contiguous item range; warps interleave inside it --------------------------------------
+    const int n_items = __ldg(prm.item_off + prm.n_utts);
+    const int begin = (int)((long long)n_items * blockIdx.x / gridDim.x);
+    const int end = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
+    int item = begin + warp;
+    if (item >= end) return;
+    int u = find_utt(prm.item_off, prm.n_utts, item);
+    int u_first = __ldg(prm.item_off + u), u_last = __ldg(prm.item_off + u + 1);
+
+    constexpr int n_streams = (MODE == kModeMfccPower) ? 2 : 1;
+    for (; item < end; item += kExtractWarps) {
+        while (item >= u_last) { ++u; u_first = u_last; u_last = __ldg(prm.item_off + u + 1); }
+        const long long s0 = __ldg(prm.utt_off + u);
+        const int n = (int)(__ldg(prm.utt_off + u + 1) - s0);
+        const long long f0 = __ldg(prm.frame_off + u);
+        const int T = (int)(__ldg(prm.frame_off + u + 1) - f0);
+        const int t0 = (item - u_first) * G::FPW;
+        const float* wav = prm.wav + s0;
+
+#pragma unroll 1
+        for (int stream = 0; stream < n_streams; ++stream) {
+            const int deriv = (MODE == kModeMfccPower) ? stream : prm.deriv;
+            __syncwarp();                                        // previous mel reads of P / pass-1 reads of stage done
+            stage_item<G>(lane, wav, n, t0, hop, deriv, stage);
+            __syncwarp();
+            pass1<G>(lane, stage, hop, win2, Y);
+            __syncwarp();
+#pragma unroll 1
+            for (int task = lane; task < G::P2_TASKS; task += 32) pass2_row<G>(task, Y);
+            __syncwarp();
+#pragma unroll 1
+            for (int k2 = 0; k2 <= 12; ++k2) {
+                pk2 a, b;
+                const bool on = split_load<G>(lane, k2, Y, tws, a, b);
+                __syncwarp();                                    // every lane holds its Z before P overwrites the rows
+                if (on) split_store<G>(lane, k2, P, a, b);
+            }
+            __syncwarp();
+
+            // ---- sparse mel + log + store ---------------------------------------------------------------
+            float vmax = 0.f;
+            for (int task = lane; task < G::PPW * n_mels; task += 32) {
+                const int p = task / n_mels, m = task - p * n_mels;
+                const pk2 acc = mel_band(P + p * (2 * G::YP), taps, band_ptr[m], band_ptr[m + 1]);
+                const int ta = t0 + 2 * p;
+                const float va = lo(acc), vb = hi(acc);
+                if (MODE == kModeDbFrameMajor) {
+                    float* o = prm.out + (f0 + ta) * n_mels + m;
+                    if (ta < T) o[0] = power_to_db(va);
+                    if (ta + 1 < T) o[n_mels] = power_to_db(vb);
+                } else if (MODE == kModeDbBandMajor) {
+                    float* o = prm.out + f0 * n_mels + (long long)m * T + ta;
+                    if (ta < T) o[0] = power_to_db(va);
+                    if (ta + 1 < T) o[1] = power_to_db(vb);
+                } else {                                          // raw mel power, frame major, per stream
+                    float* o = prm.out + ((long long)stream * prm.total_frames + f0 + ta) * n_mels + m;
+                    if (ta < T) { o[0] = va; vmax = fmaxf(vmax, va); }
+                    if (ta + 1 < T) { o[n_mels] = vb; vmax = fmaxf(vmax, vb); }
+                }
+            }
+            if (MODE == kModeMfccPower) {
+                // per-utterance max of the mel power (top_db floor, functional.py:393-402); non-negative floats
+                // order like their bit patterns
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+                if (lane == 0) atomicMax(prm.utt_max + (long long)stream * prm.n_utts + u, __float_as_int(vmax));
+            }
+        }
+    }
+}
+
+// ---- MFCC phase 2: dB with the per-utterance floor, then DCT (transforms/_transforms.py:714-717) ------------
+// One CTA handles kDctFrames consecutive global frames (they may straddle utterances).  Thread (f = tid % 32,
+// q = tid / 32) produces coefficients [10q, 10q+10) of the three streams of frame f.
+constexpr int kDctFrames = 32;
+constexpr int kDctThreads = 128;
+
+__global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctParams prm) {
+    constexpr int NM = 128, NC = 40, DS = 44;                    // D row stride (floats), keeps float2 alignment
+    extern __shared__ __align__(16) unsigned char dct_smem[];
+    float* D = reinterpret_cast<float*>(dct_smem);                                   // [NM][DS]
+    float (*X)[kDctFrames][NM + 1] = reinterpret_cast<float (*)[kDctFrames][NM + 1]>(D + NM * DS);
+    int* frame_utt = reinterpret_cast<int*>(D + NM * DS + 2 * kDctFrames * (NM + 1));
+    const long long g0 = (long long)blockIdx.x * kDctFrames;
+    for (int i = threadIdx.x; i < NM * NC; i += kDctThreads) D[(i / NC) * DS + (i % NC)] = prm.dct[i];
+    for (int i = threadIdx.x; i < 2 * kDctFrames * NM; i += kDctThreads) {
+        const int s = i / (kDctFrames * NM), r = i % (kDctFrames * NM), f = r / NM, m = r % NM;
+        const long long g = g0 + f;
+        X[s][f][m] = g < prm.total_frames ? prm.power[((long long)s * prm.total_frames + g) * NM + m] : 0.f;
+    }
+    if (threadIdx.x < kDctFrames) {
+        const long long g = g0 + threadIdx.x;
+        int lo_ = 0, hi_ = prm.n_utts - 1;
+        while (lo_ < hi_) {
+            const int mid = (lo_ + hi_) >> 1;
+            if (prm.frame_off[mid + 1] > g) hi_ = mid; else lo_ = mid + 1;
+        }
+        frame_utt[threadIdx.x] = lo_;
+    }
+    __syncthreads();
+    const int f = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const long long g = g0 + f;
+    if (g >= prm.total_frames) return;
+    const int u = frame_utt[f];
+    const float max0 = __int_as_float(prm.utt_max[u]), max1 = __int_as_float(prm.utt_max[prm.n_utts + u]);
+    const float floor0 = power_to_db(max0) - prm.top_db;
+    const float floor1 = power_to_db(max1) - prm.top_db;
+    const float floor2 = power_to_db(0.25f * max1) - prm.top_db;
+    float acc[3][10];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int c = 0; c < 10; ++c) acc[s][c] = 0.f;
+    for (int m = 0; m < NM; ++m) {
+        const float p0 = X[0][f][m], p1 = X[1][f][m];
+        const float d0 = fmaxf(power_to_db(p0), floor0);
+        const float d1 = fmaxf(power_to_db(p1), floor1);
+        const float d2 = fmaxf(power_to_db(0.25f * p1), floor2);   // np.gradient(x, 2) == np.gradient(x) / 2 exactly
+        const float* drow = D + m * DS + 10 * q;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+            const float w = drow[c];
+            acc[0][c] = fmaf(d0, w, acc[0][c]);
+            acc[1][c] = fmaf(d1, w, acc[1][c]);
+            acc[2][c] = fmaf(d2, w, acc[2][c]);
+        }
+    }
+    const long long f0 = prm.frame_off[u];
+    const int T = (int)(prm.frame_off[u + 1] - f0);
+    const int t = (int)(g - f0);
+    float* o = prm.out + f0 * (3 * NC) + t;
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int c = 0; c < 10; ++c) o[(long long)(s * NC + 10 * q + c) * T] = acc[s][c];
+}
+
+// ---- host launchers ----------------------------------------------------------------------------------------
+template <int R>
+static size_t extract_smem_bytes(int hop, int n_taps, int n_mels) {
+    using G = Geo<R>;
+    const int span4 = (G::span(hop) + 3) & ~3;
+    const size_t const_bytes = (13 * R * 16 + G::NC * 8 + (size_t)n_taps * 8 + (n_mels + 1) * 4 + 15) & ~(size_t)15;
+    return const_bytes + (size_t)ExtractWarps<R>::value * (span4 * 4 + G::Y_PK4 * 16);
+}
+
+template <int R, int MODE>
+static cudaError_t launch_one(const ExtractParams& prm, int grid, cudaStream_t stream) {
+    const size_t smem = extract_smem_bytes<R>(prm.hop, prm.n_taps, prm.n_mels);
+    cudaError_t e = cudaFuncSetAttribute(extract_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    extract_kernel<R, MODE><<<grid, ExtractWarps<R>::value * 32, smem, stream>>>(prm);
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_mode(const ExtractParams& prm, int mode, int grid, cudaStream_t stream) {
+    switch (mode) {
+        case kModeDbFrameMajor: return launch_one<R, kModeDbFrameMajor>(prm, grid, stream);
+        case kModeDbBandMajor: return launch_one<R, kModeDbBandMajor>(prm, grid, stream);
+        case kModeMfccPower: return launch_one<R, kModeMfccPower>(prm, grid, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_extract(const ExtractParams& prm, int n_fft, int mode, int grid, cudaStream_t stream) {
+    switch (n_fft) {
+        case 400: return launch_mode<8>(prm, mode, grid, stream);
+        case 800: return launch_mode<16>(prm, mode, grid, stream);
+        case 1600: return launch_mode<32>(prm, mode, grid, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+int extract_frames_per_item(int n_fft) {
+    switch (n_fft) {
+        case 400: return Geo<8>::FPW;
+        case 800: return Geo<16>::FPW;
+        case 1600: return Geo<32>::FPW;
+    }
+    return 0;
+}
+
+size_t extract_smem_bytes_for(int n_fft, int hop, int n_taps, int n_mels) {
+    switch (n_fft) {
+        case 400: return extract_smem_bytes<8>(hop, n_taps, n_mels);
+        case 800: return extract_smem_bytes<16>(hop, n_taps, n_mels);
+        case 1600: return extract_smem_bytes<32>(hop, n_taps, n_mels);
+    }
+    return 0;
+}
+
+cudaError_t launch_mfcc_dct(const MfccDctParams& prm, cudaStream_t stream) {
+    const long long blocks = (prm.total_frames + kDctFrames - 1) / kDctFrames;
+    if (blocks == 0) return cudaSuccess;
+    const size_t smem = (128 * 44 + 2 * kDctFrames * 129 + kDctFrames) * 4;
+    cudaError_t e = cudaFuncSetAttribute(mfcc_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mfcc_dct_kernel<<<(unsigned)blocks, kDctThreads, smem, stream>>>(prm);
+    return cudaGetLastError();
+}
+
+}  // namespace sept

@@ -1,0 +1,120 @@
+"""Batched B200 feature extraction: the new ragged-batch entry points above the C ABI.
+
+The reference extracts one utterance per Python call on the CPU (feature_extraction/audio_feature_extraction.py:
+180-189).  Here a whole batch of utterances is one ragged device buffer and one kernel launch per feature.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SAMPLE_RATE = 16000
+HOP_MEL = 160            # audio_feature_extraction.py:32
+N_FFT_MFCC, HOP_MFCC, N_MFCC = 400, 200, 40   # torchaudio MFCC defaults used by audio_feature_extraction.py:17
+
+
+@dataclass
+class Layout:
+    """Frame / work-item offsets of a ragged batch for one (n_fft, hop)."""
+    frame_off_host: np.ndarray       # int64 [n+1]
+    frame_off: torch.Tensor          # device int64 [n+1]
+    item_off: torch.Tensor           # device int32 [n+1]
+
+    @property
+    def total_frames(self) -> int:
+        return int(self.frame_off_host[-1])
+
+    def frames(self, u: int) -> int:
+        return int(self.frame_off_host[u + 1] - self.frame_off_host[u])
+
+
+class RaggedAudio:
+    """Utterances back to back in one device buffer: wav[utt_off[u]:utt_off[u+1]] (16 kHz mono fp32)."""
+
+    def __init__(self, wav: torch.Tensor, utt_off_host: np.ndarray):
+        _lib.require_cuda(wav)
+        if wav.dtype != torch.float32 or wav.dim() != 1 or not wav.is_contiguous():
+            raise ValueError("wav must be a contiguous 1-D float32 tensor")
+        self.wav = wav
+        self.utt_off_host = np.ascontiguousarray(utt_off_host, dtype=np.int64)
+        if self.utt_off_host.ndim != 1 or len(self.utt_off_host) < 1 or self.utt_off_host[-1] > wav.numel():
+            raise ValueError("utt_off must be a 1-D offset array within wav")
+        self.utt_off = torch.from_numpy(self.utt_off_host).to(wav.device, non_blocking=True)
+        self._layouts: dict[tuple[int, int], Layout] = {}
+
+    @classmethod
+    def from_list(cls, waves: Sequence, device="cuda") -> "RaggedAudio":
+        arrs = [np.asarray(w.detach().cpu() if torch.is_tensor(w) else w, dtype=np.float32).reshape(-1) for w in waves]
+        off = np.zeros(len(arrs) + 1, dtype=np.int64)
+        np.cumsum([len(a) for a in arrs], out=off[1:])
+        host = torch.from_numpy(np.concatenate(arrs) if arrs else np.zeros(0, np.float32))
+        return cls(host.to(device), off)
+
+    @property
+    def n_utts(self) -> int:
+        return len(self.utt_off_host) - 1
+
+    def layout(self, n_fft: int, hop: int) -> Layout:
+        key = (n_fft, hop)
+        if key not in self._layouts:
+            n = self.n_utts
+            frame_off = np.zeros(n + 1, dtype=np.int64)
+            item_off = np.zeros(n + 1, dtype=np.int32)
+            _lib.check(_lib.lib().sept_extract_layout(self.utt_off_host.ctypes.data, n, n_fft, hop,
+                                                      frame_off.ctypes.data, item_off.ctypes.data))
+            dev = self.wav.device
+            self._layouts[key] = Layout(frame_off, torch.from_numpy(frame_off).to(dev), torch.from_numpy(item_off).to(dev))
+        return self._layouts[key]
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def logmel(batch: RaggedAudio, n_fft: int = 800, n_mels: int = 128, hop: int = HOP_MEL, band_major: bool = False,
+           deriv: bool = False, out: torch.Tensor | None = None) -> tuple[torch.Tensor, Layout]:
+    """log-mel dB of every utterance of the batch (the arithmetic of mel_spectrogram(), reference :29-46).
+
+    Returns (features, layout).  Frame-major (default): features is (total_frames, n_mels) and utterance u is rows
+    layout.frame_off[u]:layout.frame_off[u+1] -- the (T, 128) matrix preprocess_adversary_data.py:345 builds with
+    mel1[0].T.  band_major: flat buffer whose utterance u is an (n_mels, T_u) block at frame_off[u] * n_mels.
+    """
+    lay = batch.layout(n_fft, hop)
+    dev = batch.wav.device
+    if out is None:
+        shape = (lay.total_frames * n_mels,) if band_major else (lay.total_frames, n_mels)
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sept_logmel_f32(batch.wav.data_ptr(), batch.utt_off.data_ptr(), lay.frame_off.data_ptr(),
+                                              lay.item_off.data_ptr(), batch.n_utts, n_fft, hop, n_mels, int(deriv),
+                                              1 if band_major else 0, out.data_ptr(), _stream(dev)))
+    return out, lay
+
+
+def mfcc(batch: RaggedAudio, out: torch.Tensor | None = None) -> tuple[torch.Tensor, Layout]:
+    """MFCC-40 of x, np.gradient(x) and np.gradient(x, 2) (the arithmetic of mfcc(), reference :15-26).
+
+    Returns (flat, layout): utterance u is the (120, T_u) block flat[frame_off[u]*120 : frame_off[u+1]*120]."""
+    lay = batch.layout(N_FFT_MFCC, HOP_MFCC)
+    dev = batch.wav.device
+    tf = lay.total_frames
+    if out is None:
+        out = torch.empty(tf * 3 * N_MFCC, dtype=torch.float32, device=dev)
+    scratch = torch.empty(2 * tf * 128, dtype=torch.float32, device=dev)
+    utt_max = torch.empty(2 * batch.n_utts, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sept_mfcc_f32(batch.wav.data_ptr(), batch.utt_off.data_ptr(), lay.frame_off.data_ptr(),
+                                            lay.item_off.data_ptr(), batch.n_utts, tf, scratch.data_ptr(),
+                                            utt_max.data_ptr(), out.data_ptr(), _stream(dev)))
+    return out, lay
+
+
+def split_band_major(flat: torch.Tensor, lay: Layout, rows: int) -> list[torch.Tensor]:
+    """Views (rows, T_u) of a band-major flat buffer, one per utterance."""
+    fo = lay.frame_off_host
+    return [flat[fo[u] * rows:fo[u + 1] * rows].view(rows, -1) for u in range(len(fo) - 1)]
