@@ -1,0 +1,334 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline metric of BASELINE.json on synthetic data: log-mel audio-hours/sec (n_fft 800, hop 160,
+128 mels) over an IEMOCAP-sized corpus, plus cloak+GRL training utterances/sec as a secondary figure.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One step = one pass of the extraction hot path over one corpus-sized ragged batch (5531 utterances, 2-10 s each,
+~9.2 audio-hours, 2.1 GB of fp32 waveform -- larger than the 126 MB L2, so no flush is needed between steps).
+N > 1 (torchrun, one rank per GPU): every rank extracts its own corpus-sized shard, no data-path collective
+("scaling": "weak"); the time is the max over ranks of the CUDA-event time of the K steps.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+N_FFT, HOP, N_MELS = 800, 160, 128
+CORPUS_UTTS = 5531                         # IEMOCAP 4-class size
+FLOP_PER_FRAME = 22999                     # log-mel n_fft=800 (rFFT 2.5 N log2 N + window + power + mel + log)
+BYTES_PER_FRAME = 4 * HOP + 4 * N_MELS     # waveform read once + features written once = 1152 B
+FP32_LANES_PER_SM = 128
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def corpus_lengths(n_utts: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return rng.integers(2 * 16000, 10 * 16000 + 1, size=n_utts).astype(np.int64)
+
+
+def synth_corpus_device(lengths: np.ndarray, seed: int, device) -> torch.Tensor:
+    """Speech-shaped synthetic audio generated on the device (workload generation, outside every timed region):
+    white noise -> 1/sqrt(f) tilt -> 3-5 Hz syllabic envelope -> peak 0.3, per utterance."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    total = int(lengths.sum())
+    wav = torch.empty(total, dtype=torch.float32, device=device)
+    pos = 0
+    for n in lengths.tolist():
+        white = torch.randn(n, generator=g, device=device)
+        spec = torch.fft.rfft(white)
+        f = torch.fft.rfftfreq(n, 1.0 / 16000, device=device)
+        tilt = torch.where(f > 0, torch.rsqrt(torch.clamp(f, min=1e-6)), torch.zeros_like(f))
+        x = torch.fft.irfft(spec * tilt, n)
+        fm = 3.0 + 2.0 * float(torch.rand(1, generator=g, device=device))
+        t = torch.arange(n, device=device, dtype=torch.float32) / 16000.0
+        x = x * (0.5 * (1.0 + torch.sin(2.0 * np.pi * fm * t)))
+        wav[pos:pos + n] = x * (0.3 / x.abs().max().clamp_min(1e-12))
+        pos += n
+    return wav
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except ValueError:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path (oracle/ref_port.py, torchaudio)
+# --------------------------------------------------------------------------------------------------------------
+def cpu_sample_waves(n_utts: int, seed: int):
+    from speech_emotion_privacy_trust_b200 import synth
+    rng = np.random.default_rng(seed)
+    lens = corpus_lengths(n_utts, seed)
+    return [torch.from_numpy(synth.speech_shaped(int(n), rng))[None] for n in lens]
+
+
+def time_cpu_reference(waves, threads: int) -> float:
+    """Seconds for one pass of the reference's per-utterance loop (audio_feature_extraction.py:180-186, mel1 only)."""
+    from oracle import ref_port
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    for a in waves:
+        ref_port.mel_spectrogram(a, n_fft=N_FFT, feature_len=N_MELS)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = 240                                  # ~0.4 audio-hours per step: about a second of CPU work
+    waves = cpu_sample_waves(n_sample, 1234)
+    hours = sum(a.shape[1] for a in waves) / 16000 / 3600
+    for _ in range(args.warmup):
+        time_cpu_reference(waves, threads)
+    t = [time_cpu_reference(waves, threads) for _ in range(args.steps)]
+    total = sum(t)
+    value = hours * args.steps / total
+    sample = f"{n_sample} utterances ({hours:.3f} audio-h) of the seed-1234 corpus per step, one utterance per call"
+    print(json.dumps({
+        "impl": "reference", "metric": "log-mel audio-hours/sec", "value": value, "unit": "audio-hours/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world, note="reference arm: bounded sample of the same workload on the host cores"),
+        "cpu_baseline": {"value": value, "unit": "audio-hours/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(world: int, note: str | None = None):
+    cfg = {"workload": f"log-mel n_fft={N_FFT} hop={HOP} n_mels={N_MELS} (mel_spectrogram, mel1) over a synthetic "
+                       f"IEMOCAP-sized corpus: {CORPUS_UTTS} utterances of 2-10 s at 16 kHz per GPU (BASELINE.json configs[0] "
+                       "shape, batched as in configs[3])",
+           "utterances_per_gpu": CORPUS_UTTS, "n_fft": N_FFT, "hop": HOP, "n_mels": N_MELS,
+           "layout": "frame-major (T,128) per utterance", "sharding": f"utterances, {world} rank(s), no collective",
+           "l2": "inputs (2.1 GB/step) larger than L2, no flush needed"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from speech_emotion_privacy_trust_b200 import _lib, extraction
+
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().sept_init(N_MELS))
+
+    lengths = corpus_lengths(args.utts, 1234 + rank)
+    utt_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    wav = synth_corpus_device(lengths, 4321 + rank, dev)
+    batch = extraction.RaggedAudio(wav, utt_off)
+    lay = batch.layout(N_FFT, HOP)
+    frames = lay.total_frames
+    hours = float(lengths.sum()) / 16000 / 3600
+    out = torch.empty((frames, N_MELS), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        extraction.logmel(batch, n_fft=N_FFT, n_mels=N_MELS, hop=HOP, out=out)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t0 = time.perf_counter()
+    evs[0].record()
+    for k in range(args.steps):
+        extraction.logmel(batch, n_fft=N_FFT, n_mels=N_MELS, hop=HOP, out=out)
+        evs[k + 1].record()
+    barrier()
+    t1 = time.perf_counter()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    kernel_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]     # one launch per step on this stream
+    clocks = sampler.window(t0, t1) if sampler else None
+
+    # ---- end to end through the public API with HOST buffers ("e2e") ----------------------------------------
+    host_wav = torch.empty(wav.numel(), dtype=torch.float32, pin_memory=True)
+    host_wav.copy_(wav)
+    host_out = torch.empty((frames, N_MELS), dtype=torch.float32, pin_memory=True)
+    e2e_steps = max(2, min(args.steps, 5))
+    extraction.logmel_host(host_wav, utt_off, n_fft=N_FFT, n_mels=N_MELS, hop=HOP, out_host=host_out, device=dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        extraction.logmel_host(host_wav, utt_off, n_fft=N_FFT, n_mels=N_MELS, hop=HOP, out_host=host_out, device=dev)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    if not torch.equal(host_out[:1000], out[:1000].cpu()):
+        raise SystemExit("bench.py: end-to-end result differs from the device-resident result")
+
+    # ---- max over ranks --------------------------------------------------------------------------------------
+    stats = torch.tensor([total_ms, e2e_ms, hours, float(frames)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(mx[0]), float(mx[1])
+        hours_all, frames_all = float(sm[2]), float(sm[3])
+    else:
+        hours_all, frames_all = hours, float(frames)
+
+    extras = {}
+    if rank == 0 or world > 1:
+        try:
+            extras = secondary_metrics(args, dev, rank, world)
+        except Exception as exc:                                   # the headline number must not depend on the extras
+            extras = {"error": f"{type(exc).__name__}: {exc}"}
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        fp32_peak = sms * FP32_LANES_PER_SM * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        k_ms = statistics.mean(kernel_ms)
+        ach_tf = FLOP_PER_FRAME * frames / (k_ms * 1e-3) / 1e12
+        ach_gbs = BYTES_PER_FRAME * frames / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "log-mel audio-hours/sec", "value": hours_all * args.steps / (total_ms * 1e-3), "unit": "audio-hours/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": hours_all / (e2e_ms * 1e-3), "unit": "audio-hours/s", "h2d_bytes_per_step": int(wav.numel() * 4),
+                    "d2h_bytes_per_step": int(frames * N_MELS * 4), "ms_per_step": e2e_ms,
+                    "api": "extraction.logmel_host(pinned host wav, utt_off) -> pinned host (frames,128)"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
+                         "traffic": None, "kernel": "extract_kernel<16, frame-major>", "kernel_ms": k_ms,
+                         "algorithmic_flop_per_frame": FLOP_PER_FRAME, "frames_per_launch": frames,
+                         "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json ({peak_src}); "
+                                        "the path is FP32-CUDA-core bound, not HBM or tensor bound (SURVEY 8d)",
+                         "hbm": {"achieved": ach_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": ach_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_frame": BYTES_PER_FRAME}},
+            "extras": extras,
+        }
+        line["cpu_baseline"] = cpu_baseline() if world == 1 else None
+        print(json.dumps(line))
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    threads = os.cpu_count() or 1
+    n_sample = 1200
+    waves = cpu_sample_waves(n_sample, 1234)
+    hours = sum(a.shape[1] for a in waves) / 16000 / 3600
+    time_cpu_reference(waves[:50], threads)
+    best = min(time_cpu_reference(waves, threads) for _ in range(2))
+    return {"value": hours / best, "unit": "audio-hours/s", "cores": threads, "kind": "port",
+            "sample": f"first {n_sample} utterances ({hours:.2f} audio-h) of the seed-1234 corpus, reference loop "
+                      "(one utterance per call, transforms built per call), best of 2"}
+
+
+def secondary_metrics(args, dev, rank, world):
+    """BASELINE.json's second figure: cloak+GRL training utterances/sec (config 3), data parallel, B=32 per GPU."""
+    from benchmarks_train import train_throughput
+    return train_throughput(dev, rank, world, steps=20, warmup=5)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--utts", type=int, default=CORPUS_UTTS, help="utterances per GPU (debug only; the metric is quoted on the default)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""Secondary figure of BASELINE.json: cloak + GRL training utterances/sec (config 3), measured by bench.py.
+
+One step = what training_cloak_with_grl.train() does per batch (reference :122-169): H2D of the batch, cloak forward,
+frozen emotion classifier + gender adversary through gradient reversal, speaker-weighted cross-entropies
+(emotion + gender_lambda * gender, /B), backward, one flat-bucket gradient all-reduce (N > 1), SGD step, loss read back.
+B = 32 per GPU (reference default :212), two_d_cnn_lstm h=64, random-init weights, synthetic z-normed windows."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def build_model(dev, grl_lambda=0.1, seed=8):
+    from speech_emotion_privacy_trust_b200 import dropin
+    dropin.install()
+    import baseline_models
+    import cloak_models
+    torch.manual_seed(seed)
+    mk = lambda pred: baseline_models.two_d_cnn_lstm(1, 128, 5, lstm_hidden_size=64, num_layers_lstm=2, pred=pred,
+                                                     bidirectional=True, rnn_cell="gru", global_feature=0)
+    noise = cloak_models.cloak_noise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 10.0, dev)
+    return cloak_models.two_d_cnn_lstm_syn_with_grl(mk("emotion"), mk("gender"), noise, grl_lambda).to(dev)
+
+
+def weighted_losses(p_emo, p_gen, emo, gen, w, gender_lambda):
+    """sum_i CE(emotion_i) * w_i / B + gender_lambda * CE(gender_i) * w_i / B  (reference :141-154, one launch per term
+    instead of 2B)."""
+    ce = torch.nn.functional.cross_entropy
+    b = p_emo.shape[0]
+    return ((ce(p_emo, emo, reduction="none") + gender_lambda * ce(p_gen, gen, reduction="none")) * w).sum() / b
+
+
+def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32):
+    import torch.distributed as dist
+    from speech_emotion_privacy_trust_b200 import parallel, synth
+    model = build_model(dev).train()
+    parallel.broadcast_parameters(model)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=1e-4)      # reference :417
+    x, emo, gen, spk = synth.cloak_windows(batch * 4, seed=8 + rank)
+    hx = torch.from_numpy(x).pin_memory()
+    hemo, hgen = torch.from_numpy(emo).pin_memory(), torch.from_numpy(gen).pin_memory()
+    w = torch.ones(batch, device=dev)
+    loss_host = torch.empty(1, pin_memory=True)
+
+    def step(i):
+        s = (i % 4) * batch
+        xb = hx[s:s + batch].to(dev, non_blocking=True)
+        eb, gb = hemo[s:s + batch].to(dev, non_blocking=True), hgen[s:s + batch].to(dev, non_blocking=True)
+        p1, p2, _ = model(xb, pooling="mean")
+        loss = weighted_losses(p1, p2, eb, gb, w, 0.1)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        parallel.allreduce_gradients(params)
+        opt.step()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    n_params = sum(p.numel() for p in params)
+    return {"metric": "cloak+GRL train utterances/sec", "value": batch * world * steps / (ms * 1e-3), "unit": "utterances/s",
+            "ms_per_step": ms / steps, "per_gpu_batch": batch, "global_batch": batch * world, "steps": steps,
+            "model": "two_d_cnn_lstm_syn_with_grl(two_d_cnn_lstm h=64 x2)", "trainable_params": n_params,
+            "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0, "final_loss": float(loss_host[0]),
+            "h2d_bytes_per_step": int(batch * 200 * 128 * 4 + batch * 16), "includes": "H2D batch, fwd, bwd, all-reduce, SGD, loss D2H"}

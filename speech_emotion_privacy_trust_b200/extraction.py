@@ -118,3 +118,85 @@ def split_band_major(flat: torch.Tensor, lay: Layout, rows: int) -> list[torch.T
     """Views (rows, T_u) of a band-major flat buffer, one per utterance."""
     fo = lay.frame_off_host
     return [flat[fo[u] * rows:fo[u + 1] * rows].view(rows, -1) for u in range(len(fo) - 1)]
+
+
+# ---- host-buffer entry point: copies pipelined against the kernel ----------------------------------------------
+_PINNED: dict[tuple[str, int], torch.Tensor] = {}
+
+
+def _pinned_i64(tag: str, n: int) -> torch.Tensor:
+    t = _PINNED.get((tag, 0))
+    if t is None or t.numel() < n:
+        t = torch.empty(max(n, 1024), dtype=torch.int64, pin_memory=True)
+        _PINNED[(tag, 0)] = t
+    return t[:n]
+
+
+def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 800, n_mels: int = 128, hop: int = HOP_MEL,
+                out_host: torch.Tensor | None = None, device="cuda", chunk_samples: int = 1 << 25, n_streams: int = 3):
+    """log-mel dB for a ragged batch that lives in HOST memory, result back in host memory (frame-major).
+
+    The batch is cut into chunks of about `chunk_samples` samples at utterance boundaries; each chunk is copied to the
+    device, extracted and copied back on one of `n_streams` streams, so the H2D copy, the kernel and the D2H copy of
+    neighbouring chunks overlap (PCIe is full duplex).  Pass pinned tensors to get asynchronous copies.
+    Returns (out_host, frame_off_host)."""
+    dev = torch.device(device)
+    if wav_host.is_cuda or wav_host.dtype != torch.float32 or wav_host.dim() != 1:
+        raise ValueError("wav_host must be a 1-D float32 host tensor")
+    lib = _lib.lib()
+    off = np.ascontiguousarray(utt_off_host, dtype=np.int64)
+    n = len(off) - 1
+    frame_off = np.zeros(n + 1, dtype=np.int64)
+    item_off = np.zeros(n + 1, dtype=np.int32)
+    _lib.check(lib.sept_extract_layout(off.ctypes.data, n, n_fft, hop, frame_off.ctypes.data, item_off.ctypes.data))
+    total_frames = int(frame_off[-1])
+    if out_host is None:
+        out_host = torch.empty((total_frames, n_mels), dtype=torch.float32, pin_memory=True)
+    # chunk boundaries at utterance starts
+    bounds = [0]
+    while bounds[-1] < n:
+        a = bounds[-1]
+        b = int(np.searchsorted(off, off[a] + chunk_samples, side="right")) - 1
+        bounds.append(min(n, max(b, a + 1)))
+    n_chunks = len(bounds) - 1
+    # all per-chunk offset tables in one pinned buffer, one H2D copy
+    per = [(bounds[c], bounds[c + 1]) for c in range(n_chunks)]
+    words = sum(3 * (b - a + 1) for a, b in per)
+    tab_host = _pinned_i64("tab", words)
+    pos, slots = 0, []
+    for a, b in per:
+        k = b - a + 1
+        tab_host[pos:pos + k] = torch.from_numpy(off[a:b + 1] - off[a])
+        tab_host[pos + k:pos + 2 * k] = torch.from_numpy(frame_off[a:b + 1] - frame_off[a])
+        tab_host[pos + 2 * k:pos + 3 * k].view(torch.int32)[:k] = torch.from_numpy(item_off[a:b + 1] - item_off[a])
+        slots.append((pos, k))
+        pos += 3 * k
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        tab_dev = tab_host.to(dev, non_blocking=True)
+        max_samples = max(int(off[b] - off[a]) for a, b in per)
+        max_frames = max(int(frame_off[b] - frame_off[a]) for a, b in per)
+        streams = [torch.cuda.Stream(dev) for _ in range(min(n_streams, n_chunks))]
+        bufs = [(torch.empty(max_samples, dtype=torch.float32, device=dev),
+                 torch.empty((max_frames, n_mels), dtype=torch.float32, device=dev)) for _ in streams]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for c, (a, b) in enumerate(per):
+            s = streams[c % len(streams)]
+            wbuf, obuf = bufs[c % len(streams)]
+            ns, nf = int(off[b] - off[a]), int(frame_off[b] - frame_off[a])
+            p, k = slots[c]
+            with torch.cuda.stream(s):
+                if c < len(streams):
+                    s.wait_event(ready)
+                wbuf[:ns].copy_(wav_host[off[a]:off[b]], non_blocking=True)
+                base = tab_dev.data_ptr() + 8 * p
+                _lib.check(lib.sept_logmel_f32(wbuf.data_ptr(), base, base + 8 * k, base + 16 * k, b - a, n_fft, hop, n_mels,
+                                               0, 0, obuf.data_ptr(), s.cuda_stream))
+                out_host[frame_off[a]:frame_off[b]].copy_(obuf[:nf], non_blocking=True)
+        for s in streams:
+            main.wait_stream(s)
+        for wbuf, obuf in bufs:
+            wbuf.record_stream(main)
+            obuf.record_stream(main)
+    return out_host, frame_off

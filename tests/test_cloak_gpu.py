@@ -1,0 +1,167 @@
+"""GPU parity of the fused cloak / gradient-reversal kernels against the golden vectors of the real reference modules
+(eps supplied externally; north_star tolerance 1e-6) and of the drop-in modules against a plain PyTorch fp32
+composition of the same ops."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from speech_emotion_privacy_trust_b200 import dropin
+    dropin.install()
+    import baseline_models
+    import cloak_models
+    import reversal_gradient
+    return cloak_models, reversal_gradient, baseline_models
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("tag", ["nomask", "mask"])
+def test_cloak_layer_golden_forward_backward(mods, golden_cloak, tag):
+    cloak_models, reversal_gradient, _ = mods
+    g = golden_cloak
+    mn, mx, lam = float(g["min_scale"]), float(g["max_scale"]), float(g["lambda"])
+    layer = cloak_models.cloak_noise(_t(g[f"{tag}_locs"]).cpu(), torch.ones(g[f"{tag}_locs"].shape), mn, mx, "cuda").cuda()
+    with torch.no_grad():
+        layer.rhos.copy_(_t(g[f"{tag}_rhos"]))
+    layer.external_eps = _t(g[f"{tag}_eps"])
+    mask = _t(g["mask_mask"]) if tag == "mask" else None
+    x = _t(g[f"{tag}_x"]).requires_grad_(True)
+    assert float((layer.scales() - _t(g[f"{tag}_sigma"])).abs().max()) < TOL
+    # (a) the reference's own composition: cloak layer, then a separate GradientReversal on one branch
+    y = layer(x, mask) if mask is not None else layer(x)
+    assert float((y - _t(g[f"{tag}_out"])).abs().max()) < TOL
+    y_rev = reversal_gradient.GradientReversalFunction.apply(y, lam)
+    ((y * _t(g[f"{tag}_g_a"])).sum() + (y_rev * _t(g[f"{tag}_g_b"])).sum()).backward()
+    for got, key in ((layer.locs.grad, "dlocs"), (layer.rhos.grad, "drhos"), (x.grad, "dx")):
+        scale = max(1.0, float(np.abs(g[f"{tag}_{key}"]).max()))
+        assert float((got - _t(g[f"{tag}_{key}"])).abs().max()) < TOL * scale * 4, key
+    # (b) the fused twin: one backward kernel takes both upstream gradients and applies -lambda itself
+    layer.zero_grad()
+    x2 = _t(g[f"{tag}_x"]).requires_grad_(True)
+    ya, yb = layer.forward_with_reversed_twin(x2, mask, lam)
+    assert torch.equal(ya, y.detach()) and ya.data_ptr() == yb.data_ptr()
+    ((ya * _t(g[f"{tag}_g_a"])).sum() + (yb * _t(g[f"{tag}_g_b"])).sum()).backward()
+    for got, key in ((layer.locs.grad, "dlocs"), (layer.rhos.grad, "drhos"), (x2.grad, "dx")):
+        scale = max(1.0, float(np.abs(g[f"{tag}_{key}"]).max()))
+        assert float((got - _t(g[f"{tag}_{key}"])).abs().max()) < TOL * scale * 4, key
+
+
+def test_gradient_reversal_golden(mods, golden_cloak):
+    _, reversal_gradient, _ = mods
+    g = golden_cloak
+    z = _t(g["grl_g"] * 0 + 1.0).requires_grad_(True)
+    out = reversal_gradient.GradientReversal(float(g["grl_lambda"]))(z)
+    assert torch.equal(out, z)
+    out.backward(_t(g["grl_g"]))
+    assert np.array_equal(z.grad.cpu().numpy(), g["grl_dx"])      # bit exact: one fp32 multiply
+    assert reversal_gradient.ReverseLayerF is reversal_gradient.GradientReversalFunction
+
+
+def test_cloak_full_size_vs_torch_fp32(mods):
+    """B=64, W=200, F=128 (config 2) against the same formula written with torch ops in fp32 on the GPU."""
+    cloak_models, _, _ = mods
+    torch.manual_seed(3)
+    B, W, F = 64, 200, 128
+    layer = cloak_models.cloak_noise(0.1 * torch.randn(1, W, F), torch.ones(1, W, F), 0.01, 5.0, "cuda").cuda()
+    with torch.no_grad():
+        layer.rhos.add_(torch.randn(1, W, F, device="cuda"))
+    eps = 0.1 * torch.randn(1, W, F, device="cuda")
+    layer.external_eps = eps
+    mask = (torch.rand(1, W, F, device="cuda") > 0.4).float()
+    x = torch.randn(B, 1, W, F, device="cuda", requires_grad=True)
+    ga, gb, lam = torch.randn(B, 1, W, F, device="cuda"), torch.randn(B, 1, W, F, device="cuda"), 0.1
+    ya, yb = layer.forward_with_reversed_twin(x, mask, lam)
+    ((ya * ga).sum() + (yb * gb).sum()).backward()
+    got = (ya.detach().clone(), layer.locs.grad.clone(), layer.rhos.grad.clone(), x.grad.clone())
+    layer.zero_grad()
+    xr = x.detach().clone().requires_grad_(True)
+    ref_y = xr * mask + (layer.locs + layer.scales() * (eps * mask))
+    gtot = ga - lam * gb
+    (ref_y * gtot).sum().backward()
+    assert float((got[0] - ref_y.detach()).abs().max()) < TOL
+    assert float((got[3] - xr.grad).abs().max()) < TOL
+    # batch reductions of 64 O(1) terms: compare to an fp64 sum, allow a few fp32 ulps of the sum's magnitude
+    d64 = gtot.double().sum(0)
+    assert float((got[1].double() - d64).abs().max()) < 2e-5
+    assert float((got[1] - layer.locs.grad).abs().max()) < 2e-5
+    assert float((got[2] - layer.rhos.grad).abs().max()) < 2e-5 * max(1.0, float(layer.rhos.grad.abs().max()))
+    # deterministic reduction
+    layer.zero_grad()
+    ya, yb = layer.forward_with_reversed_twin(x, mask, lam)
+    ((ya * ga).sum() + (yb * gb).sum()).backward()
+    assert torch.equal(layer.locs.grad, got[1]) and torch.equal(layer.rhos.grad, got[2])
+
+
+def test_device_philox_noise(mods):
+    cloak_models, _, _ = mods
+    torch.manual_seed(8)
+    layer = cloak_models.cloak_noise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 10.0, "cuda").cuda()
+    x = torch.zeros(4, 1, 200, 128, device="cuda")
+    sig = layer.scales().detach()
+    e1 = (layer(x)[0] / sig)                                   # locs = 0 -> y = sigma * eps
+    e2 = (layer(x)[0] / sig)
+    assert abs(float(e1.mean())) < 2e-3 and abs(float(e1.std()) - 0.1) < 2e-3      # N(0, 0.1), 25 600 samples
+    assert not torch.equal(e1, e2)                              # a fresh sample per forward ...
+    y = layer(x)
+    assert torch.equal(y[0], y[3])                              # ... shared by the whole batch (cloak_models.py:47)
+    torch.manual_seed(8)
+    again = cloak_models.cloak_noise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 10.0, "cuda").cuda()
+    assert torch.equal(again(x)[0] / sig, e1)                   # same seed, same draw index -> same eps on every rank
+    n = layer.sample_noise()
+    assert n.shape == (1, 200, 128) and n.requires_grad
+    k = float(((e1.flatten() / 0.1) ** 4).mean())
+    assert 2.7 < k < 3.3                                        # Gaussian kurtosis
+
+
+def test_grl_model_matches_unfused_composition(mods):
+    """two_d_cnn_lstm_syn_with_grl: the fused twin path against the reference's literal composition (cloak layer ->
+    GradientReversal module -> gender conv), same weights, dropout off, eps shared."""
+    cloak_models, reversal_gradient, baseline_models = mods
+    torch.manual_seed(5)
+    mk = lambda pred: baseline_models.two_d_cnn_lstm(1, 128, 5, lstm_hidden_size=64, pred=pred, global_feature=0)
+    noise = cloak_models.cloak_noise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 10.0, "cuda")
+    model = cloak_models.two_d_cnn_lstm_syn_with_grl(mk("emotion"), mk("gender"), noise, 0.1).cuda().train()
+    for mod in model.modules():
+        if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.GRU):
+            mod.dropout = 0.0
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eval()
+    eps = 0.1 * torch.randn(1, 200, 128, device="cuda")
+    model.intermed.external_eps = eps
+    x = torch.randn(8, 1, 200, 128, device="cuda")
+    emo, gen = torch.randint(0, 4, (8,), device="cuda"), torch.randint(0, 2, (8,), device="cuda")
+    ce = torch.nn.functional.cross_entropy
+
+    def grads(fused):
+        model.zero_grad()
+        if fused:
+            p1, p2, noisy = model(x, pooling="mean")
+        else:
+            y = model.intermed(x)
+            noisy = y.detach()
+            z1 = baseline_models.sequence_features(model.original_model, y).mean(dim=1)
+            p1 = baseline_models.classify(model.original_model, z1, None, pred="emotion")
+            z2 = baseline_models.sequence_features(model.gender_model, y).mean(dim=1)     # conv = Sequential(GRL, conv)
+            p2 = baseline_models.classify(model.gender_model, z2, None, pred="gender")
+        (ce(p1, emo) + 0.1 * ce(p2, gen)).backward()
+        conv_w = model.gender_model.conv[1][0].weight.grad.clone()
+        return p1.detach(), p2.detach(), noisy, model.intermed.locs.grad.clone(), model.intermed.rhos.grad.clone(), conv_w
+
+    a, b = grads(True), grads(False)
+    assert a[0].shape == (8, 4) and a[1].shape == (8, 2) and a[2].shape == (8, 1, 200, 128)
+    assert torch.equal(a[2], b[2])
+    for i, name in ((0, "preds1"), (1, "preds2"), (3, "dlocs"), (4, "drhos"), (5, "gender conv wgrad")):
+        scale = max(1e-3, float(b[i].abs().max()))
+        assert float((a[i] - b[i]).abs().max()) < 2e-3 * scale, name     # cuDNN conv/GRU (TF32-capable) sit in between
+    assert all(p.grad is None for p in model.original_model.parameters())
