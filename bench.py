@@ -257,7 +257,9 @@ def run_b200(args):
         hours_all, frames_all = hours, float(frames)
 
     extras = {}
-    if rank == 0 or world > 1:
+    if args.no_extras:
+        extras = {"skipped": True}
+    elif rank == 0 or world > 1:
         try:
             extras = secondary_metrics(args, dev, rank, world)
         except Exception as exc:                                   # the headline number must not depend on the extras
@@ -289,7 +291,7 @@ def run_b200(args):
                                  "frac": ach_gbs / peaks.get("hbm_gbs", 6650.0), "algorithmic_bytes_per_frame": BYTES_PER_FRAME}},
             "extras": extras,
         }
-        line["cpu_baseline"] = cpu_baseline() if world == 1 else None
+        line["cpu_baseline"] = cpu_baseline() if (world == 1 and not args.no_extras) else None
         print(json.dumps(line))
     if sampler:
         sampler.stop()
@@ -322,6 +324,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary metric, e2e and cpu_baseline (profiling runs)")
     ap.add_argument("--utts", type=int, default=CORPUS_UTTS, help="utterances per GPU (debug only; the metric is quoted on the default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -19,6 +19,11 @@ namespace sept {
 constexpr float kDbPerLog2 = 3.01029995663981195f;   // 10*log10(2)
 constexpr float kAmin = 1e-10f;                        // amplitude_to_DB amin (functional.py:390)
 
+// bytes of the CTA-shared constants: split twiddles, mel weight quads, band descriptors, window
+__host__ __device__ inline int extract_const_bytes(int R, int n_wquads, int n_mels) {
+    return 13 * R * 16 + n_wquads * 16 + n_mels * 16 + R * 25 * 8;
+}
+
 __device__ __forceinline__ float power_to_db(float p) { return kDbPerLog2 * __log2f(fmaxf(p, kAmin)); }
 
 // first utterance u with item_off[u+1] > item
@@ -31,32 +36,48 @@ __device__ __forceinline__ int find_utt(const int32_t* __restrict__ item_off, in
     return lo_;
 }
 
+// ---- asynchronous staging (LDGSTS): the next item's waveform span lands in shared memory while the current item is
+// still in its shared-memory phases ----------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct ItemRef {
+    const float* wav;      // utterance start
+    long long f0;          // first output frame of the utterance
+    int n, T, t0, u;
+    bool interior;
+};
+
 template <int R, int MODE>
 __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel(const ExtractParams prm) {
     using G = Geo<R>;
-    constexpr int kExtractWarps = ExtractWarps<R>::value;
+    const int kExtractWarps = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int hop = prm.hop, n_mels = prm.n_mels;
-    const int span4 = (G::span(hop) + 3) & ~3;
+    const int stage_floats = G::stage_floats(hop);
 
     // ---- CTA-shared constants -----------------------------------------------------------------------------
     f4* tws = reinterpret_cast<f4*>(smem_raw);                                   // [13][R]
-    f2* win2 = reinterpret_cast<f2*>(tws + 13 * R);                              // [NC]
-    tap_t* taps = reinterpret_cast<tap_t*>(win2 + G::NC);                        // [n_taps]
-    int* band_ptr = reinterpret_cast<int*>(taps + prm.n_taps);                   // [n_mels + 1]
-    const int const_bytes = (13 * R * 16 + G::NC * 8 + prm.n_taps * 8 + (n_mels + 1) * 4 + 15) & ~15;
+    f4* melw = tws + 13 * R;                                                     // [n_wquads]
+    band_t* bands = reinterpret_cast<band_t*>(melw + prm.n_wquads);              // [n_mels]
+    f2* win2 = reinterpret_cast<f2*>(bands + n_mels);                            // [NC]
+    const int const_bytes = extract_const_bytes(R, prm.n_wquads, n_mels);
     for (int i = threadIdx.x; i < 13 * R; i += blockDim.x) tws[i] = reinterpret_cast<const f4*>(prm.tws)[i];
+    for (int i = threadIdx.x; i < prm.n_wquads; i += blockDim.x) melw[i] = reinterpret_cast<const f4*>(prm.mel_w)[i];
+    for (int i = threadIdx.x; i < n_mels; i += blockDim.x) bands[i] = reinterpret_cast<const band_t*>(prm.mel_bands)[i];
     for (int i = threadIdx.x; i < G::NC; i += blockDim.x) win2[i] = reinterpret_cast<const f2*>(prm.window)[i];
-    for (int i = threadIdx.x; i < prm.n_taps; i += blockDim.x) taps[i] = reinterpret_cast<const tap_t*>(prm.taps)[i];
-    for (int i = threadIdx.x; i <= n_mels; i += blockDim.x) band_ptr[i] = prm.band_ptr[i];
     __syncthreads();
 
     // ---- warp-private tiles -------------------------------------------------------------------------------
-    const int warp_bytes = span4 * 4 + G::Y_PK4 * 16;
+    const int warp_bytes = stage_floats * 4 + G::Y_PK4 * 16;
     unsigned char* wbase = smem_raw + const_bytes + warp * warp_bytes;
     float* stage = reinterpret_cast<float*>(wbase);
-    pk4* Y = reinterpret_cast<pk4*>(wbase + span4 * 4);
+    pk4* Y = reinterpret_cast<pk4*>(wbase + stage_floats * 4);
     pk2* P = reinterpret_cast<pk2*>(Y);
 
     // ---- this CTA's contiguous item range; warps interleave inside it --------------------------------------
@@ -68,55 +89,91 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     int u = find_utt(prm.item_off, prm.n_utts, item);
     int u_first = __ldg(prm.item_off + u), u_last = __ldg(prm.item_off + u + 1);
 
+    auto locate = [&](int it) {
+        while (it >= u_last) { ++u; u_first = u_last; u_last = __ldg(prm.item_off + u + 1); }
+        ItemRef r;
+        const long long s0 = __ldg(prm.utt_off + u);
+        r.n = (int)(__ldg(prm.utt_off + u + 1) - s0);
+        r.f0 = __ldg(prm.frame_off + u);
+        r.T = (int)(__ldg(prm.frame_off + u + 1) - r.f0);
+        r.t0 = (it - u_first) * G::FPW;
+        r.u = u;
+        r.wav = prm.wav + s0;
+        r.interior = item_is_interior<G>(r.n, r.t0, hop);
+        return r;
+    };
+    auto prefetch = [&](const ItemRef& r) {                       // raw span + halo of an interior item -> stage[1 ..]
+        const float* src = r.wav + ((long long)r.t0 * hop - G::PAD - 1);
+        const int count = G::span(hop) + 2;
+        for (int i = lane; i < count; i += 32) cp_async_f32(stage + G::LEAD - 1 + i, src + i);
+        cp_async_commit();
+    };
+
+    ItemRef cur = locate(item);
+    if (cur.interior) prefetch(cur);
+
     constexpr int n_streams = (MODE == kModeMfccPower) ? 2 : 1;
     for (; item < end; item += kExtractWarps) {
-        while (item >= u_last) { ++u; u_first = u_last; u_last = __ldg(prm.item_off + u + 1); }
-        const long long s0 = __ldg(prm.utt_off + u);
-        const int n = (int)(__ldg(prm.utt_off + u + 1) - s0);
-        const long long f0 = __ldg(prm.frame_off + u);
-        const int T = (int)(__ldg(prm.frame_off + u + 1) - f0);
-        const int t0 = (item - u_first) * G::FPW;
-        const float* wav = prm.wav + s0;
-
 #pragma unroll 1
         for (int stream = 0; stream < n_streams; ++stream) {
             const int deriv = (MODE == kModeMfccPower) ? stream : prm.deriv;
-            __syncwarp();                                        // previous mel reads of P / pass-1 reads of stage done
-            stage_item<G>(lane, wav, n, t0, hop, deriv, stage);
-            __syncwarp();
-            pass1<G>(lane, stage, hop, win2, Y);
-            __syncwarp();
+            if (cur.interior) {
+                if (stream == 0) { cp_async_wait_all(); __syncwarp(); }
+                if (deriv) pass1<G, true>(lane, stage, hop, win2, Y);
+                else pass1<G, false>(lane, stage, hop, win2, Y);
+            } else {
+                __syncwarp();
+                stage_item<G>(lane, cur.wav, cur.n, cur.t0, hop, deriv, stage);
+                __syncwarp();
+                pass1<G, false>(lane, stage, hop, win2, Y);
+            }
+            __syncwarp();                                        // stage is free, Y is complete
+
+            ItemRef nxt = cur;
+            if (stream == n_streams - 1 && item + kExtractWarps < end) {
+                nxt = locate(item + kExtractWarps);
+                if (nxt.interior) prefetch(nxt);                 // overlaps pass 2, split and mel of this item
+            }
+
 #pragma unroll 1
             for (int task = lane; task < G::P2_TASKS; task += 32) pass2_row<G>(task, Y);
             __syncwarp();
-#pragma unroll 1
-            for (int k2 = 0; k2 <= 12; ++k2) {
-                pk2 a, b;
-                const bool on = split_load<G>(lane, k2, Y, tws, a, b);
-                __syncwarp();                                    // every lane holds its Z before P overwrites the rows
-                if (on) split_store<G>(lane, k2, P, a, b);
+
+            {   // real split + power: every Z of the item goes to registers, then the tile is overwritten by P
+                pk2 a[13], b[13];
+                bool on0 = false;
+#pragma unroll
+                for (int k2 = 0; k2 <= 12; ++k2) {
+                    const bool on = split_load<G>(lane, k2, Y, tws, a[k2], b[k2]);
+                    if (k2 == 0) on0 = on;
+                }
+                __syncwarp();
+                split_store_all<G>(lane, P, a, b, on0);
             }
             __syncwarp();
 
-            // ---- sparse mel + log + store ---------------------------------------------------------------
+            // ---- mel bands (lane = band, all frame pairs of the item) + log + store --------------------------
             float vmax = 0.f;
-            for (int task = lane; task < G::PPW * n_mels; task += 32) {
-                const int p = task / n_mels, m = task - p * n_mels;
-                const pk2 acc = mel_band(P + p * (2 * G::YP), taps, band_ptr[m], band_ptr[m + 1]);
-                const int ta = t0 + 2 * p;
-                const float va = lo(acc), vb = hi(acc);
-                if (MODE == kModeDbFrameMajor) {
-                    float* o = prm.out + (f0 + ta) * n_mels + m;
-                    if (ta < T) o[0] = power_to_db(va);
-                    if (ta + 1 < T) o[n_mels] = power_to_db(vb);
-                } else if (MODE == kModeDbBandMajor) {
-                    float* o = prm.out + f0 * n_mels + (long long)m * T + ta;
-                    if (ta < T) o[0] = power_to_db(va);
-                    if (ta + 1 < T) o[1] = power_to_db(vb);
-                } else {                                          // raw mel power, frame major, per stream
-                    float* o = prm.out + ((long long)stream * prm.total_frames + f0 + ta) * n_mels + m;
-                    if (ta < T) { o[0] = va; vmax = fmaxf(vmax, va); }
-                    if (ta + 1 < T) { o[n_mels] = vb; vmax = fmaxf(vmax, vb); }
+            for (int m = lane; m < n_mels; m += 32) {
+                pk2 acc[G::PPW];
+                mel_band<G>(P, melw, bands[m], acc);
+#pragma unroll
+                for (int p = 0; p < G::PPW; ++p) {
+                    const int ta = cur.t0 + 2 * p;
+                    const float va = lo(acc[p]), vb = hi(acc[p]);
+                    if (MODE == kModeDbFrameMajor) {
+                        float* o = prm.out + (cur.f0 + ta) * n_mels + m;
+                        if (ta < cur.T) o[0] = power_to_db(va);
+                        if (ta + 1 < cur.T) o[n_mels] = power_to_db(vb);
+                    } else if (MODE == kModeDbBandMajor) {
+                        float* o = prm.out + cur.f0 * n_mels + (long long)m * cur.T + ta;
+                        if (ta < cur.T) o[0] = power_to_db(va);
+                        if (ta + 1 < cur.T) o[1] = power_to_db(vb);
+                    } else {                                      // raw mel power, frame major, per stream
+                        float* o = prm.out + ((long long)stream * prm.total_frames + cur.f0 + ta) * n_mels + m;
+                        if (ta < cur.T) { o[0] = va; vmax = fmaxf(vmax, va); }
+                        if (ta + 1 < cur.T) { o[n_mels] = vb; vmax = fmaxf(vmax, vb); }
+                    }
                 }
             }
             if (MODE == kModeMfccPower) {
@@ -124,8 +181,10 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                 // order like their bit patterns
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-                if (lane == 0) atomicMax(prm.utt_max + (long long)stream * prm.n_utts + u, __float_as_int(vmax));
+                if (lane == 0) atomicMax(prm.utt_max + (long long)stream * prm.n_utts + cur.u, __float_as_int(vmax));
             }
+            __syncwarp();                                        // P reads done before the next pass 1 overwrites Y
+            if (stream == n_streams - 1) cur = nxt;
         }
     }
 }
@@ -197,20 +256,31 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------------
+constexpr size_t kMaxSmem = 232448;      // 227 KB opt-in limit per CTA
+
 template <int R>
-static size_t extract_smem_bytes(int hop, int n_taps, int n_mels) {
+static int extract_warps(int hop, int n_wquads, int n_mels) {     // warps whose tiles fit beside the constants
     using G = Geo<R>;
-    const int span4 = (G::span(hop) + 3) & ~3;
-    const size_t const_bytes = (13 * R * 16 + G::NC * 8 + (size_t)n_taps * 8 + (n_mels + 1) * 4 + 15) & ~(size_t)15;
-    return const_bytes + (size_t)ExtractWarps<R>::value * (span4 * 4 + G::Y_PK4 * 16);
+    const size_t cb = (size_t)extract_const_bytes(R, n_wquads, n_mels), wb = G::stage_floats(hop) * 4 + G::Y_PK4 * 16;
+    if (cb + wb > kMaxSmem) return 0;
+    const int fit = (int)((kMaxSmem - cb) / wb);
+    return fit < ExtractWarps<R>::value ? fit : ExtractWarps<R>::value;
+}
+
+template <int R>
+static size_t extract_smem_bytes(int hop, int n_wquads, int n_mels) {
+    using G = Geo<R>;
+    const int w = extract_warps<R>(hop, n_wquads, n_mels);
+    if (w == 0) return kMaxSmem + 1;
+    return (size_t)extract_const_bytes(R, n_wquads, n_mels) + (size_t)w * (G::stage_floats(hop) * 4 + G::Y_PK4 * 16);
 }
 
 template <int R, int MODE>
 static cudaError_t launch_one(const ExtractParams& prm, int grid, cudaStream_t stream) {
-    const size_t smem = extract_smem_bytes<R>(prm.hop, prm.n_taps, prm.n_mels);
+    const size_t smem = extract_smem_bytes<R>(prm.hop, prm.n_wquads, prm.n_mels);
     cudaError_t e = cudaFuncSetAttribute(extract_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    extract_kernel<R, MODE><<<grid, ExtractWarps<R>::value * 32, smem, stream>>>(prm);
+    extract_kernel<R, MODE><<<grid, extract_warps<R>(prm.hop, prm.n_wquads, prm.n_mels) * 32, smem, stream>>>(prm);
     return cudaGetLastError();
 }
 
@@ -242,11 +312,11 @@ int extract_frames_per_item(int n_fft) {
     return 0;
 }
 
-size_t extract_smem_bytes_for(int n_fft, int hop, int n_taps, int n_mels) {
+size_t extract_smem_bytes_for(int n_fft, int hop, int n_wquads, int n_mels) {
     switch (n_fft) {
-        case 400: return extract_smem_bytes<8>(hop, n_taps, n_mels);
-        case 800: return extract_smem_bytes<16>(hop, n_taps, n_mels);
-        case 1600: return extract_smem_bytes<32>(hop, n_taps, n_mels);
+        case 400: return extract_smem_bytes<8>(hop, n_wquads, n_mels);
+        case 800: return extract_smem_bytes<16>(hop, n_wquads, n_mels);
+        case 1600: return extract_smem_bytes<32>(hop, n_wquads, n_mels);
     }
     return 0;
 }

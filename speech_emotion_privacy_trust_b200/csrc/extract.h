@@ -14,7 +14,7 @@ enum : int {
 };
 
 // warps per CTA (one persistent CTA per SM); bounded by the 227 KB of shared memory the warp tiles take
-template <int R> struct ExtractWarps { static constexpr int value = (R == 16) ? 10 : 9; };
+template <int R> struct ExtractWarps { static constexpr int value = (R == 16) ? 11 : 10; };   // upper bound; the launch fits fewer if hop is large
 
 struct ExtractParams {
     const float* wav;            // all utterances back to back
@@ -24,13 +24,13 @@ struct ExtractParams {
     int n_utts;
     int hop;
     int n_mels;
-    int n_taps;
+    int n_wquads;                // float4 groups of mel weights
     int deriv;                   // dB modes: 0 waveform, 1 np.gradient(waveform)
     long long total_frames;      // kModeMfccPower only
     const float* window;         // [n_fft] periodic Hann
     const float* tws;            // [13][R][4] split twiddles
-    const void* taps;            // [n_taps] {int pos; float w}
-    const int32_t* band_ptr;     // [n_mels + 1]
+    const float* mel_w;          // [n_wquads][4] mel weights (x 1/4), zero padded band runs
+    const void* mel_bands;       // [n_mels] {int k0, w4, nq, pad}
     float* out;
     int* utt_max;                // kModeMfccPower: [2][n_utts] float bits, zeroed by the caller
 };
@@ -47,7 +47,7 @@ struct MfccDctParams {
 };
 
 cudaError_t launch_extract(const ExtractParams& prm, int n_fft, int mode, int grid, cudaStream_t stream);
-size_t extract_smem_bytes_for(int n_fft, int hop, int n_taps, int n_mels);
+size_t extract_smem_bytes_for(int n_fft, int hop, int n_wquads, int n_mels);
 int extract_frames_per_item(int n_fft);
 cudaError_t launch_mfcc_dct(const MfccDctParams& prm, cudaStream_t stream);
 

@@ -11,9 +11,11 @@
 // verified on a CPU-only box.  The host emulation is test code, not a fallback: the library has no CPU path.
 //
 // Warp-private shared memory:
-//   stage  float [SPAN = (FPW-1)*hop + n_fft]   reflect-padded waveform span of the item
+//   stage  float [2 + SPAN + 1], SPAN = (FPW-1)*hop + n_fft   reflect-padded waveform span of the item at offset 2,
+//                                                one halo sample either side (for the waveform-gradient stream)
 //   Y      pk4   [PPW][25 rows k2][YS = R+1]     pass 1 output / pass 2 in place; (re, im) x (frame a, frame b)
-//   P      pk2   aliases Y row by row            4|X[k]|^2 of the frame pair at tile position bin_pos(k)
+//   P      pk2   [PPW][NC + 8] over the Y tile   4|X[k]|^2 of the frame pair, bins in natural order (written only
+//                                                after every Z of the item has been read into registers)
 // Replaces, for one item: torch.stft framing/window/rFFT + abs().pow(2) (torchaudio functional.py:123-144)
 // and MelScale's matmul (transforms/_transforms.py:417).
 #pragma once
@@ -23,7 +25,6 @@ namespace sept {
 
 struct alignas(8) f2 { float x, y; };
 struct alignas(16) f4 { float x, y, z, w; };
-struct alignas(8) tap_t { int pos; float w; };
 struct alignas(16) pk4 { pk2 re, im; };
 
 template <int R_>
@@ -35,11 +36,12 @@ struct Geo {
     static constexpr int YS = R + 1;                              // pk4 per k2 row (odd: rows hit distinct bank groups)
     static constexpr int YP = 25 * YS + 2;                        // pk4 per pair
     static constexpr int Y_PK4 = PPW * YP;                        // pk4 per warp
-    static constexpr int NYQ_POS = R;                             // pk2 slot of bin NC (spare tail of row 0)
+    static constexpr int PP = NC + 8;                             // pk2 per pair of the power tile (bins 0..NC, natural order)
     static constexpr int P2_TASKS = PPW * 25;                     // pass-2 row tasks per item
+    static constexpr int LEAD = 2;                                // floats in front of the staged span (halo + 8-byte alignment)
+    static_assert(PPW * PP <= 2 * Y_PK4, "power tile must fit in the Y tile it overwrites");
     static SEPT_HD int span(int hop) { return (FPW - 1) * hop + NFFT; }
-    // pk2 slot (relative to the pair's Y base) of real-FFT bin k, 0 <= k <= NC
-    static SEPT_HD int bin_pos(int k) { return k == NC ? NYQ_POS : (k % 25) * (2 * YS) + (k % R); }
+    static SEPT_HD int stage_floats(int hop) { return (LEAD + span(hop) + 1 + 3) & ~3; }
 };
 
 // ---- staging: reflect-padded span of the item starting at frame t0 ----------------------------------------
@@ -60,33 +62,67 @@ SEPT_HD float staged_sample(const float* wav, int n, int src, int deriv) {
     return (wav[src + 1] - wav[src - 1]) * 0.5f;
 }
 
+// generic staging (edge items: reflection, utterance ends, one-sided differences): stage[LEAD - 1 + i] = sample at
+// padded index q0 - 1 + i, i = 0 .. span + 1.  Loads are issued in independent batches of 8 per lane.
 template <class G>
 SEPT_HD void stage_item(int lane, const float* wav, int n, int t0, int hop, int deriv, float* stage) {
-    const long long q0 = (long long)t0 * hop;
-    const int span = G::span(hop);
-    for (int i = lane; i < span; i += 32) stage[i] = staged_sample(wav, n, reflect_src(q0 + i, G::PAD, n), deriv);
+    const long long q0 = (long long)t0 * hop - 1;
+    const int count = G::span(hop) + 2;
+    for (int base = 0; base < count; base += 256) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * 32 + lane;
+            v[j] = i < count ? staged_sample(wav, n, reflect_src(q0 + i, G::PAD, n), deriv) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * 32 + lane;
+            if (i < count) stage[G::LEAD - 1 + i] = v[j];
+        }
+    }
+}
+
+// true when the staged span (with its halo) of the item lies strictly inside the utterance: no reflection, no
+// one-sided difference; such items are staged with asynchronous copies and differentiated in shared memory
+template <class G>
+SEPT_HD bool item_is_interior(int n, int t0, int hop) {
+    const long long first = (long long)t0 * hop - G::PAD - 1;          // source index of the front halo
+    return first >= 1 && first + G::span(hop) + 2 <= (long long)n - 1;
 }
 
 // ---- pass 1: lane (p, n1) windows the 25 complex samples z[n] = xw[2n] + i xw[2n+1], n = (25 n1 + R n2) mod NC,
 // of frames 2p and 2p+1 and transforms them over n2 ------------------------------------------------------------
-template <class G>
+// DIFF: the stage holds the raw waveform of an interior item and the stream wanted is np.gradient of it
+// (audio_feature_extraction.py:20): the central difference (x[j+1] - x[j-1]) / 2 is taken on the fly from the
+// neighbouring sample pairs, the 1/2 riding on the window (exact: a power of two).
+template <class G, bool DIFF>
 SEPT_HD void pass1(int lane, const float* stage, int hop, const f2* win2, pk4* Y) {
     constexpr int R = G::R;
     const int p = lane / R, n1 = lane % R;
-    const f2* xa = reinterpret_cast<const f2*>(stage + (2 * p) * hop);
-    const f2* xb = reinterpret_cast<const f2*>(stage + (2 * p + 1) * hop);
+    const f2* xa = reinterpret_cast<const f2*>(stage + G::LEAD + (2 * p) * hop);
+    const f2* xb = reinterpret_cast<const f2*>(stage + G::LEAD + (2 * p + 1) * hop);
     pk2 re[25], im[25];
 #pragma unroll
     for (int n2 = 0; n2 < 25; ++n2) {
         const int idx = Pfa<R>::in_index(n1, n2);
-        const f2 a = xa[idx], b = xb[idx], w = win2[idx];
-        re[n2] = pk(a.x * w.x, b.x * w.x);
-        im[n2] = pk(a.y * w.y, b.y * w.y);
+        const f2 w = win2[idx];
+        if (!DIFF) {
+            const f2 a = xa[idx], b = xb[idx];
+            re[n2] = pk(a.x * w.x, b.x * w.x);
+            im[n2] = pk(a.y * w.y, b.y * w.y);
+        } else {
+            const f2 al = xa[idx - 1], a = xa[idx], ar = xa[idx + 1];
+            const f2 bl = xb[idx - 1], b = xb[idx], br = xb[idx + 1];
+            const float hx = 0.5f * w.x, hy = 0.5f * w.y;
+            re[n2] = pk((a.y - al.y) * hx, (b.y - bl.y) * hx);
+            im[n2] = pk((ar.x - a.x) * hy, (br.x - b.x) * hy);
+        }
     }
     Dft<25>::run(re, im);
-    pk4* y = Y + p * G::YP + n1;
+    pk2* y = reinterpret_cast<pk2*>(Y + p * G::YP + n1);           // two 8-byte stores: no register shuffling into quads
 #pragma unroll
-    for (int k2 = 0; k2 < 25; ++k2) y[k2 * G::YS] = pk4{re[k2], im[k2]};
+    for (int k2 = 0; k2 < 25; ++k2) { y[k2 * (2 * G::YS)] = re[k2]; y[k2 * (2 * G::YS) + 1] = im[k2]; }
 }
 
 // ---- pass 2: row task (p, k2) transforms its R samples over n1, in place ----------------------------------------
@@ -99,8 +135,9 @@ SEPT_HD void pass2_row(int task, pk4* Y) {
 #pragma unroll
     for (int i = 0; i < R; ++i) { const pk4 v = y[i]; re[i] = v.re; im[i] = v.im; }
     Dft<R>::run(re, im);
+    pk2* y2 = reinterpret_cast<pk2*>(y);
 #pragma unroll
-    for (int i = 0; i < R; ++i) y[i] = pk4{re[i], im[i]};
+    for (int i = 0; i < R; ++i) { y2[2 * i] = re[i]; y2[2 * i + 1] = im[i]; }
 }
 
 // ---- real split of one conjugate pair: Zk = Z[k], Zm = Z[NC-k], tw = W_{NFFT}^k.  Returns 4|X[k]|^2 and
@@ -130,25 +167,47 @@ SEPT_HD bool split_load(int lane, int k2, const pk4* Y, const f4* tws, pk2& pk_,
     return true;
 }
 
+// after EVERY lane holds its 13 conjugate pairs in registers (warp barrier), the Y tile is overwritten by the power
+// tile: lane (p, k1) stores bins k = CRT(k1, k2) (k mod R = k1, k mod 25 = k2) and NC - k for k2 = 0..12.  Consecutive
+// lanes hit consecutive residues mod R, so the 8-byte stores are bank-conflict free.
 template <class G>
-SEPT_HD void split_store(int lane, int k2, pk2* P, pk2 pk_, pk2 pm_) {
+SEPT_HD void split_store_all(int lane, pk2* P, const pk2 (&a)[13], const pk2 (&b)[13], bool on0) {
     constexpr int R = G::R;
-    const int p = lane / R, k1 = lane % R, km = (R - k1) % R;
-    const int rb = (25 - k2) % 25;
-    pk2* base = P + p * (2 * G::YP);
-    base[k2 * (2 * G::YS) + k1] = pk_;
-    if (k2 == 0 && k1 == 0) base[G::NYQ_POS] = pm_;              // bin NC
-    else if (!(k2 == 0 && 2 * k1 == R)) base[rb * (2 * G::YS) + km] = pm_;
+    int k = (Pfa<R>::cK1 * (lane % R)) % G::NC;                  // CRT(k1, 0); + cK2 per k2 step
+    pk2* base = P + (lane / R) * G::PP;
+#pragma unroll
+    for (int k2 = 0; k2 <= 12; ++k2) {
+        if (k2 > 0 || on0) {
+            base[k] = a[k2];
+            if (k != G::NC - k) base[G::NC - k] = b[k2];         // k = 0 pairs with the Nyquist bin NC; NC/2 is its own partner
+            if (k == 0) base[G::NC + 1] = splat(0.f);            // padded band runs may read one slot past the Nyquist bin
+        }
+        k += Pfa<R>::cK2;
+        if (k >= G::NC) k -= G::NC;
+    }
 }
 
-// ---- mel: one (frame pair, band) dot product over the band's taps (MelScale, _transforms.py:417) ---------------
-SEPT_HD pk2 mel_band(const pk2* Ppair, const tap_t* taps, int lo_, int hi_) {
-    pk2 acc = splat(0.f);
-    for (int i = lo_; i < hi_; ++i) {
-        const tap_t e = taps[i];
-        acc = fma2(Ppair[e.pos], splat(e.w), acc);
+// ---- mel: band m of every frame pair of the item: dot product over the band's contiguous bins (MelScale,
+// _transforms.py:417).  info = {first bin (even), first weight quad, number of quads}; weights are padded with zeros
+// to whole quads that stay inside bins 0..NC+1 ------------------------------------------------------------------------
+struct alignas(16) band_t { int k0, w4, nq, pad; };
+
+template <class G>
+SEPT_HD void mel_band(const pk2* P, const f4* w4, band_t info, pk2 (&acc)[G::PPW]) {
+#pragma unroll
+    for (int p = 0; p < G::PPW; ++p) acc[p] = splat(0.f);
+    for (int q = 0; q < info.nq; ++q) {
+        const f4 w = w4[info.w4 + q];
+#pragma unroll
+        for (int p = 0; p < G::PPW; ++p) {
+            const pk4* src = reinterpret_cast<const pk4*>(P + p * G::PP + info.k0 + 4 * q);
+            const pk4 a = src[0], b = src[1];
+            acc[p] = fma2(a.re, splat(w.x), acc[p]);
+            acc[p] = fma2(a.im, splat(w.y), acc[p]);
+            acc[p] = fma2(b.re, splat(w.z), acc[p]);
+            acc[p] = fma2(b.im, splat(w.w), acc[p]);
+        }
     }
-    return acc;
 }
 
 }  // namespace sept

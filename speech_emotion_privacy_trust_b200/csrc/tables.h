@@ -14,7 +14,6 @@
 
 namespace sept {
 
-struct MelTap { int32_t pos; float w; };  // pos: pk2 slot in the frame pair's power tile; w: fb[k][m] * 0.25
 
 inline std::vector<float> make_hann_periodic(int n_fft) {
     // torch evaluates the angle in float32 (arange * (2*pi/N)); mirror that, take the cosine exactly
@@ -49,30 +48,36 @@ inline std::vector<float> make_mel_fbank(int n_freqs, int n_mels, int sample_rat
     return fb;
 }
 
-// pk2 slot of real-FFT bin k (0..Nc) inside one frame pair's power tile (must equal Geo<R>::bin_pos):
-// rows are k mod 25 with stride 2*(R+1), columns k mod R; the Nyquist bin k = Nc sits in the spare slot R of row 0
-inline int power_tile_pos(int k, int R) {
-    const int Nc = R * 25;
-    if (k == Nc) return R;
-    return (k % 25) * (2 * (R + 1)) + (k % R);
-}
+// mel bands as contiguous bin runs: band m covers bins k0 .. k0 + 4*nq - 1 with weights w[4*w4 ..]; k0 is even (the
+// kernel reads bin pairs with 16-byte loads), runs are padded with zero weights to whole quads and never reach past
+// bin Nc + 1 (the kernel's power tile has Nc + 8 slots).  Weights carry the 1/4 of the kernel's 4|X|^2 convention.
+struct MelBand { int32_t k0, w4, nq, pad; };
 
-// tap lists per mel band: band_ptr[m]..band_ptr[m+1] index into taps (k ascending); weights carry the 1/4 of
-// the kernel's 4|X|^2 convention
-inline void make_mel_taps(int n_fft, int n_mels, int sample_rate, std::vector<int32_t>& band_ptr,
-                          std::vector<MelTap>& taps) {
-    const int n_freqs = n_fft / 2 + 1, R = n_fft / 50;
+inline void make_mel_bands(int n_fft, int n_mels, int sample_rate, std::vector<MelBand>& bands, std::vector<float>& weights) {
+    const int n_freqs = n_fft / 2 + 1, Nc = n_fft / 2;
     std::vector<float> fb = make_mel_fbank(n_freqs, n_mels, sample_rate, 0.0, (double)(sample_rate / 2));
-    band_ptr.assign(n_mels + 1, 0);
-    taps.clear();
+    bands.assign(n_mels, MelBand{0, 0, 0, 0});
+    weights.clear();
     for (int m = 0; m < n_mels; ++m) {
-        band_ptr[m] = (int32_t)taps.size();
-        for (int k = 0; k < n_freqs; ++k) {
-            float v = fb[(size_t)k * n_mels + m];
-            if (v != 0.f) taps.push_back({power_tile_pos(k, R), v * 0.25f});
+        int lo = -1, hi = -1;
+        for (int k = 0; k < n_freqs; ++k)
+            if (fb[(size_t)k * n_mels + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
+        MelBand b{0, (int32_t)(weights.size() / 4), 0, 0};
+        if (lo >= 0) {
+            int k0 = lo & ~1;
+            int nq = (hi - k0 + 4) / 4;
+            if (k0 + 4 * nq > Nc + 2) k0 = (Nc + 2 - 4 * nq) & ~1;     // keep the run inside the tile
+            if (k0 < 0) k0 = 0;
+            b.k0 = k0;
+            b.nq = nq;
+            for (int i = 0; i < 4 * nq; ++i) {
+                const int k = k0 + i;
+                weights.push_back(k < n_freqs ? fb[(size_t)k * n_mels + m] * 0.25f : 0.f);
+            }
         }
+        bands[m] = b;
     }
-    band_ptr[n_mels] = (int32_t)taps.size();
+    while (weights.size() % 4) weights.push_back(0.f);
 }
 
 // split twiddles W_{n_fft}^{k}, k = CRT(k1, k2) for rows k2 = 0..12, columns k1 = 0..R-1, splatted for the

@@ -18,32 +18,42 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
     const int n = (int)wav.size(), n_fft = G::NFFT;
     const int T = 1 + n / hop;
     std::vector<float> win = make_hann_periodic(n_fft), tws = make_split_twiddles(n_fft);
-    std::vector<int32_t> bp;
-    std::vector<MelTap> taps;
-    make_mel_taps(n_fft, n_mels, 16000, bp, taps);
-    std::vector<float> stage(G::span(hop) + 4);
+    std::vector<MelBand> bands;
+    std::vector<float> weights;
+    make_mel_bands(n_fft, n_mels, 16000, bands, weights);
+    std::vector<float> stage(G::stage_floats(hop), 0.f);
     std::vector<pk4> Y(G::Y_PK4);
     pk2* P = reinterpret_cast<pk2*>(Y.data());
     std::vector<float> out((size_t)T * n_mels);
+    const f2* win2 = reinterpret_cast<const f2*>(win.data());
     for (int t0 = 0; t0 < T; t0 += G::FPW) {
-        for (int lane = 0; lane < 32; ++lane) stage_item<G>(lane, wav.data(), n, t0, hop, deriv, stage.data());
+        // interior items: the kernel copies the RAW span asynchronously and differentiates on the fly in pass 1;
+        // edge items: generic staging of the wanted stream
+        const bool interior = item_is_interior<G>(n, t0, hop);
         for (int lane = 0; lane < 32; ++lane)
-            pass1<G>(lane, stage.data(), hop, reinterpret_cast<const f2*>(win.data()), Y.data());
-        for (int task = 0; task < G::P2_TASKS; ++task) pass2_row<G>(task, Y.data());
-        for (int k2 = 0; k2 <= 12; ++k2) {
-            pk2 a[32], b[32];
-            bool on[32];
-            for (int lane = 0; lane < 32; ++lane)
-                on[lane] = split_load<G>(lane, k2, Y.data(), reinterpret_cast<const f4*>(tws.data()), a[lane], b[lane]);
-            for (int lane = 0; lane < 32; ++lane)
-                if (on[lane]) split_store<G>(lane, k2, P, a[lane], b[lane]);
+            stage_item<G>(lane, wav.data(), n, t0, hop, interior ? 0 : deriv, stage.data());
+        for (int lane = 0; lane < 32; ++lane) {
+            if (interior && deriv) pass1<G, true>(lane, stage.data(), hop, win2, Y.data());
+            else pass1<G, false>(lane, stage.data(), hop, win2, Y.data());
         }
-        for (int task = 0; task < G::PPW * n_mels; ++task) {
-            const int p = task / n_mels, m = task % n_mels;
-            const pk2 acc = mel_band(P + p * (2 * G::YP), reinterpret_cast<const tap_t*>(taps.data()), bp[m], bp[m + 1]);
-            const int ta = t0 + 2 * p;
-            if (ta < T) out[(size_t)ta * n_mels + m] = 10.0f * std::log10(std::fmax(lo(acc), 1e-10f));
-            if (ta + 1 < T) out[(size_t)(ta + 1) * n_mels + m] = 10.0f * std::log10(std::fmax(hi(acc), 1e-10f));
+        for (int task = 0; task < G::P2_TASKS; ++task) pass2_row<G>(task, Y.data());
+        pk2 a[32][13], b[32][13];
+        bool on0[32];
+        for (int lane = 0; lane < 32; ++lane)
+            for (int k2 = 0; k2 <= 12; ++k2) {
+                const bool on = split_load<G>(lane, k2, Y.data(), reinterpret_cast<const f4*>(tws.data()), a[lane][k2], b[lane][k2]);
+                if (k2 == 0) on0[lane] = on;
+            }
+        for (int lane = 0; lane < 32; ++lane) split_store_all<G>(lane, P, a[lane], b[lane], on0[lane]);
+        for (int m = 0; m < n_mels; ++m) {
+            pk2 acc[G::PPW];
+            band_t info{bands[m].k0, bands[m].w4, bands[m].nq, 0};
+            mel_band<G>(P, reinterpret_cast<const f4*>(weights.data()), info, acc);
+            for (int p = 0; p < G::PPW; ++p) {
+                const int ta = t0 + 2 * p;
+                if (ta < T) out[(size_t)ta * n_mels + m] = 10.0f * std::log10(std::fmax(lo(acc[p]), 1e-10f));
+                if (ta + 1 < T) out[(size_t)(ta + 1) * n_mels + m] = 10.0f * std::log10(std::fmax(hi(acc[p]), 1e-10f));
+            }
         }
     }
     FILE* f = std::fopen(out_path, "wb");
