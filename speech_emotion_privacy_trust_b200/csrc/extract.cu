@@ -10,6 +10,7 @@
 // feature_extraction/audio_feature_extraction.py:15-46 of the reference.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 #include "extract.h"
 #include "extract_core.cuh"
@@ -21,7 +22,7 @@ constexpr float kAmin = 1e-10f;                        // amplitude_to_DB amin (
 
 // bytes of the CTA-shared constants: split twiddles, mel weight quads, band descriptors, window
 __host__ __device__ inline int extract_const_bytes(int R, int n_wquads, int n_mels) {
-    return 13 * R * 16 + n_wquads * 16 + n_mels * 16 + R * 25 * 8;
+    return (n_wquads * 16 + n_mels * 16 + R * 25 * 8 + 13 * (R + 1) * 8 + 15) & ~15;
 }
 
 __device__ __forceinline__ float power_to_db(float p) { return kDbPerLog2 * __log2f(fmaxf(p, kAmin)); }
@@ -52,8 +53,8 @@ struct ItemRef {
     bool interior;
 };
 
-template <int R, int MODE>
-__global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel(const ExtractParams prm) {
+template <int R, int MODE, int WMAX>
+__global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractParams prm) {
     using G = Geo<R>;
     const int kExtractWarps = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -62,12 +63,12 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     const int stage_floats = G::stage_floats(hop);
 
     // ---- CTA-shared constants -----------------------------------------------------------------------------
-    f4* tws = reinterpret_cast<f4*>(smem_raw);                                   // [13][R]
-    f4* melw = tws + 13 * R;                                                     // [n_wquads]
+    f4* melw = reinterpret_cast<f4*>(smem_raw);                                  // [n_wquads]
     band_t* bands = reinterpret_cast<band_t*>(melw + prm.n_wquads);              // [n_mels]
     f2* win2 = reinterpret_cast<f2*>(bands + n_mels);                            // [NC]
+    f2* tws = win2 + G::NC;                                                      // [13][R + 1]
     const int const_bytes = extract_const_bytes(R, prm.n_wquads, n_mels);
-    for (int i = threadIdx.x; i < 13 * R; i += blockDim.x) tws[i] = reinterpret_cast<const f4*>(prm.tws)[i];
+    for (int i = threadIdx.x; i < 13 * G::TWS; i += blockDim.x) tws[i] = reinterpret_cast<const f2*>(prm.tws)[i];
     for (int i = threadIdx.x; i < prm.n_wquads; i += blockDim.x) melw[i] = reinterpret_cast<const f4*>(prm.mel_w)[i];
     for (int i = threadIdx.x; i < n_mels; i += blockDim.x) bands[i] = reinterpret_cast<const band_t*>(prm.mel_bands)[i];
     for (int i = threadIdx.x; i < G::NC; i += blockDim.x) win2[i] = reinterpret_cast<const f2*>(prm.window)[i];
@@ -135,11 +136,23 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                 if (nxt.interior) prefetch(nxt);                 // overlaps pass 2, split and mel of this item
             }
 
+            if constexpr (R <= 16) {
+                // fused pass 2 + real split + power: rows j and 25-j stay in registers; the tile is overwritten by P only
+                // after every lane has loaded its rows
+                constexpr int ROUNDS = (G::PS_TASKS + 31) / 32;
+                pk2 pu[ROUNDS][R], pv[ROUNDS][R];
+#pragma unroll
+                for (int r = 0; r < ROUNDS; ++r)
+                    if (lane + 32 * r < G::PS_TASKS) pass2_split<G>(lane + 32 * r, Y, tws, pu[r], pv[r]);
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < ROUNDS; ++r)
+                    if (lane + 32 * r < G::PS_TASKS) pass2_split_store<G>(lane + 32 * r, P, pu[r], pv[r]);
+            } else {
 #pragma unroll 1
-            for (int task = lane; task < G::P2_TASKS; task += 32) pass2_row<G>(task, Y);
-            __syncwarp();
-
-            {   // real split + power: every Z of the item goes to registers, then the tile is overwritten by P
+                for (int task = lane; task < G::P2_TASKS; task += 32) pass2_row<G>(task, Y);
+                __syncwarp();
+                // real split + power: every Z of the item goes to registers, then the tile is overwritten by P
                 pk2 a[13], b[13];
                 bool on0 = false;
 #pragma unroll
@@ -258,13 +271,20 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
 // ---- host launchers ----------------------------------------------------------------------------------------
 constexpr size_t kMaxSmem = 232448;      // 227 KB opt-in limit per CTA
 
+// tuning knob (bench experiments only): SEPT_EXTRACT_WARPS=8 selects the 8-warp / 255-register build of the kernel
+static int warp_cap(int r_default) {
+    static const int env = [] { const char* e = getenv("SEPT_EXTRACT_WARPS"); return e ? atoi(e) : 0; }();
+    return (env > 0 && env < r_default) ? env : r_default;
+}
+
 template <int R>
 static int extract_warps(int hop, int n_wquads, int n_mels) {     // warps whose tiles fit beside the constants
     using G = Geo<R>;
     const size_t cb = (size_t)extract_const_bytes(R, n_wquads, n_mels), wb = G::stage_floats(hop) * 4 + G::Y_PK4 * 16;
     if (cb + wb > kMaxSmem) return 0;
     const int fit = (int)((kMaxSmem - cb) / wb);
-    return fit < ExtractWarps<R>::value ? fit : ExtractWarps<R>::value;
+    const int cap = warp_cap(ExtractWarps<R>::value);
+    return fit < cap ? fit : cap;
 }
 
 template <int R>
@@ -278,9 +298,11 @@ static size_t extract_smem_bytes(int hop, int n_wquads, int n_mels) {
 template <int R, int MODE>
 static cudaError_t launch_one(const ExtractParams& prm, int grid, cudaStream_t stream) {
     const size_t smem = extract_smem_bytes<R>(prm.hop, prm.n_wquads, prm.n_mels);
-    cudaError_t e = cudaFuncSetAttribute(extract_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int warps = extract_warps<R>(prm.hop, prm.n_wquads, prm.n_mels);
+    auto kern = warps <= 8 ? extract_kernel<R, MODE, 8> : extract_kernel<R, MODE, ExtractWarps<R>::value>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    extract_kernel<R, MODE><<<grid, extract_warps<R>(prm.hop, prm.n_wquads, prm.n_mels) * 32, smem, stream>>>(prm);
+    kern<<<grid, warps * 32, smem, stream>>>(prm);
     return cudaGetLastError();
 }
 

@@ -14,8 +14,8 @@
 //   stage  float [2 + SPAN + 1], SPAN = (FPW-1)*hop + n_fft   reflect-padded waveform span of the item at offset 2,
 //                                                one halo sample either side (for the waveform-gradient stream)
 //   Y      pk4   [PPW][25 rows k2][YS = R+1]     pass 1 output / pass 2 in place; (re, im) x (frame a, frame b)
-//   P      pk2   [PPW][NC + 8] over the Y tile   4|X[k]|^2 of the frame pair, bins in natural order (written only
-//                                                after every Z of the item has been read into registers)
+//   P      pk2   [PPW][PP] over the Y tile       4|X[k]|^2 of the frame pair at bin_pos(k) (written only after every Z
+//                                                of the item has been read into registers)
 // Replaces, for one item: torch.stft framing/window/rFFT + abs().pow(2) (torchaudio functional.py:123-144)
 // and MelScale's matmul (transforms/_transforms.py:417).
 #pragma once
@@ -36,11 +36,17 @@ struct Geo {
     static constexpr int YS = R + 1;                              // pk4 per k2 row (odd: rows hit distinct bank groups)
     static constexpr int YP = 25 * YS + 2;                        // pk4 per pair
     static constexpr int Y_PK4 = PPW * YP;                        // pk4 per warp
-    static constexpr int PP = NC + 8;                             // pk2 per pair of the power tile (bins 0..NC, natural order)
+    static constexpr int PP = NC + 2 * (NC / 16) + 8;             // pk2 per pair of the power tile (bins 0..NC+3, see bin_pos)
+    static constexpr int TWS = R + 1;                             // f2 per split-twiddle row (odd: rows spread over banks)
+    static constexpr int PS_TASKS = PPW * 13;                     // fused pass-2 + split tasks per item (R <= 16)
     static constexpr int P2_TASKS = PPW * 25;                     // pass-2 row tasks per item
     static constexpr int LEAD = 2;                                // floats in front of the staged span (halo + 8-byte alignment)
     static_assert(PPW * PP <= 2 * Y_PK4, "power tile must fit in the Y tile it overwrites");
     static SEPT_HD int span(int hop) { return (FPW - 1) * hop + NFFT; }
+    // pk2 slot of bin k in a pair's power tile: natural order with a 16-byte gap after every 16 bins, so that bins
+    // with equal k mod 16 (the same k1 of different rows) fall into different banks while quads of 4 bins starting
+    // at a multiple of 4 stay contiguous for the mel loads
+    static SEPT_HD int bin_pos(int k) { return k + ((k >> 4) << 1); }
     static SEPT_HD int stage_floats(int hop) { return (LEAD + span(hop) + 1 + 3) & ~3; }
 };
 
@@ -155,16 +161,74 @@ SEPT_HD void split_pair(pk4 zk, pk4 zm, pk2 twr, pk2 twi, pk2& pk_, pk2& pm_) {
 // iteration k2 (0..12) of the split: lane (p, k1) pairs Z at (k1, k2) with Z at (R-k1, 25-k2).
 // Returns false when the lane has nothing to do (row 0 is its own partner: only k1 <= R/2 work).
 template <class G>
-SEPT_HD bool split_load(int lane, int k2, const pk4* Y, const f4* tws, pk2& pk_, pk2& pm_) {
+SEPT_HD bool split_load(int lane, int k2, const pk4* Y, const f2* tws, pk2& pk_, pk2& pm_) {
     constexpr int R = G::R;
     const int p = lane / R, k1 = lane % R, km = (R - k1) % R;
     if (k2 == 0 && k1 > R / 2) return false;
     const int rb = (25 - k2) % 25;
     const pk4 zk = Y[p * G::YP + k2 * G::YS + k1];
     const pk4 zm = Y[p * G::YP + rb * G::YS + km];
-    const f4 tw = tws[k2 * R + k1];
-    split_pair(zk, zm, pk(tw.x, tw.y), pk(tw.z, tw.w), pk_, pm_);
+    const f2 tw = tws[k2 * G::TWS + k1];
+    split_pair(zk, zm, splat(tw.x), splat(tw.y), pk_, pm_);
     return true;
+}
+
+// zero-weight padding of the last band's run reads bins NC+1 .. NC+3: keep them finite
+template <class G>
+SEPT_HD void zero_tail(pk2* base) {
+#pragma unroll
+    for (int i = 1; i <= 3; ++i) base[G::bin_pos(G::NC + i)] = splat(0.f);
+}
+
+// ---- fused pass 2 + split (R <= 16): task (p, j) transforms rows j and 25-j of pair p over n1 in registers and
+// splits them against each other without another trip through shared memory.  pu[k1] = 4|X|^2 at bin CRT(k1, j),
+// pv[k1] = 4|X|^2 at bin CRT(k1, 25-j).  Row 0 (j = 0) is its own partner: pu holds the whole row and pv[0] the
+// Nyquist bin. ------------------------------------------------------------------------------------------------------
+template <class G>
+SEPT_HD void pass2_split(int task, const pk4* Y, const f2* tws, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
+    constexpr int R = G::R;
+    const int p = task / 13, j = task % 13, rb = (25 - j) % 25;
+    const pk4* yu = Y + p * G::YP + j * G::YS;
+    const pk4* yv = Y + p * G::YP + rb * G::YS;
+    pk2 ur[R], ui[R], vr[R], vi[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) { const pk4 a = yu[i]; ur[i] = a.re; ui[i] = a.im; }
+#pragma unroll
+    for (int i = 0; i < R; ++i) { const pk4 a = yv[i]; vr[i] = a.re; vi[i] = a.im; }
+    Dft<R>::run(ur, ui);
+    Dft<R>::run(vr, vi);
+    const f2* tw = tws + j * G::TWS;
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) {
+        constexpr int dummy = 0; (void)dummy;
+        const int km = (R - k1) % R;
+        const f2 w = tw[k1];
+        split_pair(pk4{ur[k1], ui[k1]}, pk4{vr[km], vi[km]}, splat(w.x), splat(w.y), pu[k1], pv[km]);
+    }
+}
+
+template <class G>
+SEPT_HD void pass2_split_store(int task, pk2* P, const pk2 (&pu)[G::R], const pk2 (&pv)[G::R]) {
+    constexpr int R = G::R, NC = G::NC;
+    const int p = task / 13, j = task % 13, rb = (25 - j) % 25;
+    pk2* base = P + p * G::PP;
+    const int kj = (Pfa<R>::cK2 * j) % NC, kb = (Pfa<R>::cK2 * rb) % NC;
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) {
+        const int c1 = (Pfa<R>::cK1 * k1) % NC;                  // compile-time after unrolling
+        int k = kj + c1;
+        if (k >= NC) k -= NC;
+        base[G::bin_pos(k)] = pu[k1];
+        if (j > 0) {
+            int kk = kb + c1;
+            if (kk >= NC) kk -= NC;
+            base[G::bin_pos(kk)] = pv[k1];
+        }
+    }
+    if (j == 0) {
+        base[G::bin_pos(NC)] = pv[0];
+        zero_tail<G>(base);
+    }
 }
 
 // after EVERY lane holds its 13 conjugate pairs in registers (warp barrier), the Y tile is overwritten by the power
@@ -178,9 +242,9 @@ SEPT_HD void split_store_all(int lane, pk2* P, const pk2 (&a)[13], const pk2 (&b
 #pragma unroll
     for (int k2 = 0; k2 <= 12; ++k2) {
         if (k2 > 0 || on0) {
-            base[k] = a[k2];
-            if (k != G::NC - k) base[G::NC - k] = b[k2];         // k = 0 pairs with the Nyquist bin NC; NC/2 is its own partner
-            if (k == 0) base[G::NC + 1] = splat(0.f);            // padded band runs may read one slot past the Nyquist bin
+            base[G::bin_pos(k)] = a[k2];
+            if (k != G::NC - k) base[G::bin_pos(G::NC - k)] = b[k2];   // k = 0 pairs with the Nyquist bin NC; NC/2 is its own partner
+            if (k == 0) zero_tail<G>(base);
         }
         k += Pfa<R>::cK2;
         if (k >= G::NC) k -= G::NC;
@@ -188,7 +252,7 @@ SEPT_HD void split_store_all(int lane, pk2* P, const pk2 (&a)[13], const pk2 (&b
 }
 
 // ---- mel: band m of every frame pair of the item: dot product over the band's contiguous bins (MelScale,
-// _transforms.py:417).  info = {first bin (even), first weight quad, number of quads}; weights are padded with zeros
+// _transforms.py:417).  info = {first bin (multiple of 4), first weight quad, number of quads}; weights are padded with zeros
 // to whole quads that stay inside bins 0..NC+1 ------------------------------------------------------------------------
 struct alignas(16) band_t { int k0, w4, nq, pad; };
 
@@ -200,7 +264,7 @@ SEPT_HD void mel_band(const pk2* P, const f4* w4, band_t info, pk2 (&acc)[G::PPW
         const f4 w = w4[info.w4 + q];
 #pragma unroll
         for (int p = 0; p < G::PPW; ++p) {
-            const pk4* src = reinterpret_cast<const pk4*>(P + p * G::PP + info.k0 + 4 * q);
+            const pk4* src = reinterpret_cast<const pk4*>(P + p * G::PP + G::bin_pos(info.k0 + 4 * q));
             const pk4 a = src[0], b = src[1];
             acc[p] = fma2(a.re, splat(w.x), acc[p]);
             acc[p] = fma2(a.im, splat(w.y), acc[p]);

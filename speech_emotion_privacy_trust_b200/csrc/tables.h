@@ -48,9 +48,9 @@ inline std::vector<float> make_mel_fbank(int n_freqs, int n_mels, int sample_rat
     return fb;
 }
 
-// mel bands as contiguous bin runs: band m covers bins k0 .. k0 + 4*nq - 1 with weights w[4*w4 ..]; k0 is even (the
-// kernel reads bin pairs with 16-byte loads), runs are padded with zero weights to whole quads and never reach past
-// bin Nc + 1 (the kernel's power tile has Nc + 8 slots).  Weights carry the 1/4 of the kernel's 4|X|^2 convention.
+// mel bands as contiguous bin runs: band m covers bins k0 .. k0 + 4*nq - 1 with weights w[4*w4 ..]; k0 is a multiple
+// of 4, runs are padded with zero weights to whole quads and never reach past bin Nc + 3 (the kernel's power tile keeps
+// bins Nc+1 .. Nc+3 at zero).  Weights carry the 1/4 of the kernel's 4|X|^2 convention.
 struct MelBand { int32_t k0, w4, nq, pad; };
 
 inline void make_mel_bands(int n_fft, int n_mels, int sample_rate, std::vector<MelBand>& bands, std::vector<float>& weights) {
@@ -64,10 +64,8 @@ inline void make_mel_bands(int n_fft, int n_mels, int sample_rate, std::vector<M
             if (fb[(size_t)k * n_mels + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
         MelBand b{0, (int32_t)(weights.size() / 4), 0, 0};
         if (lo >= 0) {
-            int k0 = lo & ~1;
-            int nq = (hi - k0 + 4) / 4;
-            if (k0 + 4 * nq > Nc + 2) k0 = (Nc + 2 - 4 * nq) & ~1;     // keep the run inside the tile
-            if (k0 < 0) k0 = 0;
+            const int k0 = lo & ~3;                                      // quads never straddle the tile's 16-bin blocks
+            const int nq = (hi - k0 + 4) / 4;                            // last bin read: k0 + 4*nq - 1 <= Nc + 3
             b.k0 = k0;
             b.nq = nq;
             for (int i = 0; i < 4 * nq; ++i) {
@@ -80,19 +78,18 @@ inline void make_mel_bands(int n_fft, int n_mels, int sample_rate, std::vector<M
     while (weights.size() % 4) weights.push_back(0.f);
 }
 
-// split twiddles W_{n_fft}^{k}, k = CRT(k1, k2) for rows k2 = 0..12, columns k1 = 0..R-1, splatted for the
-// packed arithmetic: 4 floats (cos, cos, -sin, -sin) per entry, row stride R
+// split twiddles W_{n_fft}^{k}, k = CRT(k1, k2) for rows k2 = 0..12, columns k1 = 0..R-1: (cos, -sin) pairs, row
+// stride R + 1 pairs (Geo<R>::TWS)
 inline std::vector<float> make_split_twiddles(int n_fft) {
-    const int R = n_fft / 50, Nc = R * 25;
-    std::vector<float> tw((size_t)13 * R * 4, 0.f);
+    const int R = n_fft / 50, Nc = R * 25, TWS = R + 1;
+    std::vector<float> tw((size_t)13 * TWS * 2, 0.f);
     for (int k2 = 0; k2 <= 12; ++k2)
         for (int k1 = 0; k1 < R; ++k1) {
             int k = -1;
             for (int c = 0; c < Nc; ++c) if (c % R == k1 && c % 25 == k2) { k = c; break; }
             double ang = -2.0 * M_PI * (double)k / (double)n_fft;
-            float* e = &tw[((size_t)k2 * R + k1) * 4];
-            e[0] = e[1] = (float)std::cos(ang);
-            e[2] = e[3] = (float)std::sin(ang);
+            tw[((size_t)k2 * TWS + k1) * 2 + 0] = (float)std::cos(ang);
+            tw[((size_t)k2 * TWS + k1) * 2 + 1] = (float)std::sin(ang);
         }
     return tw;
 }

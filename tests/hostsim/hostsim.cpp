@@ -36,15 +36,22 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
             if (interior && deriv) pass1<G, true>(lane, stage.data(), hop, win2, Y.data());
             else pass1<G, false>(lane, stage.data(), hop, win2, Y.data());
         }
-        for (int task = 0; task < G::P2_TASKS; ++task) pass2_row<G>(task, Y.data());
-        pk2 a[32][13], b[32][13];
-        bool on0[32];
-        for (int lane = 0; lane < 32; ++lane)
-            for (int k2 = 0; k2 <= 12; ++k2) {
-                const bool on = split_load<G>(lane, k2, Y.data(), reinterpret_cast<const f4*>(tws.data()), a[lane][k2], b[lane][k2]);
-                if (k2 == 0) on0[lane] = on;
-            }
-        for (int lane = 0; lane < 32; ++lane) split_store_all<G>(lane, P, a[lane], b[lane], on0[lane]);
+        const f2* tw2 = reinterpret_cast<const f2*>(tws.data());
+        if constexpr (R <= 16) {
+            static pk2 pu[G::PS_TASKS][R], pv[G::PS_TASKS][R];
+            for (int task = 0; task < G::PS_TASKS; ++task) pass2_split<G>(task, Y.data(), tw2, pu[task], pv[task]);
+            for (int task = 0; task < G::PS_TASKS; ++task) pass2_split_store<G>(task, P, pu[task], pv[task]);
+        } else {
+            for (int task = 0; task < G::P2_TASKS; ++task) pass2_row<G>(task, Y.data());
+            pk2 a[32][13], b[32][13];
+            bool on0[32];
+            for (int lane = 0; lane < 32; ++lane)
+                for (int k2 = 0; k2 <= 12; ++k2) {
+                    const bool on = split_load<G>(lane, k2, Y.data(), tw2, a[lane][k2], b[lane][k2]);
+                    if (k2 == 0) on0[lane] = on;
+                }
+            for (int lane = 0; lane < 32; ++lane) split_store_all<G>(lane, P, a[lane], b[lane], on0[lane]);
+        }
         for (int m = 0; m < n_mels; ++m) {
             pk2 acc[G::PPW];
             band_t info{bands[m].k0, bands[m].w4, bands[m].nq, 0};
