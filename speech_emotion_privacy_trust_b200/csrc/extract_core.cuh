@@ -36,17 +36,24 @@ struct Geo {
     static constexpr int YS = R + 1;                              // pk4 per k2 row (odd: rows hit distinct bank groups)
     static constexpr int YP = 25 * YS + 2;                        // pk4 per pair
     static constexpr int Y_PK4 = PPW * YP;                        // pk4 per warp
-    static constexpr int PP = NC + 2 * (NC / 16) + 8;             // pk2 per pair of the power tile (bins 0..NC+3, see bin_pos)
+    static constexpr int PP = (NC + NC / 16 + 12) & ~1;           // pk2 per pair of the power tile (bins 0..NC+3, see bin_pos)
     static constexpr int TWS = R + 1;                             // f2 per split-twiddle row (odd: rows spread over banks)
-    static constexpr int PS_TASKS = PPW * 13;                     // fused pass-2 + split tasks per item (R <= 16)
+    static constexpr int PS_ROUNDS = (PPW + 1) / 2;               // fused pass-2 + split: lane = (pair p % 2, row pair j < 13)
     static constexpr int P2_TASKS = PPW * 25;                     // pass-2 row tasks per item
     static constexpr int LEAD = 2;                                // floats in front of the staged span (halo + 8-byte alignment)
     static_assert(PPW * PP <= 2 * Y_PK4, "power tile must fit in the Y tile it overwrites");
     static SEPT_HD int span(int hop) { return (FPW - 1) * hop + NFFT; }
-    // pk2 slot of bin k in a pair's power tile: natural order with a 16-byte gap after every 16 bins, so that bins
-    // with equal k mod 16 (the same k1 of different rows) fall into different banks while quads of 4 bins starting
-    // at a multiple of 4 stay contiguous for the mel loads
-    static SEPT_HD int bin_pos(int k) { return k + ((k >> 4) << 1); }
+    // pk2 slot of bin k in a pair's power tile: natural order with one 8-byte gap after every 16 bins.  Bins with
+    // equal k mod 16 (the same k1 of different rows j, which the lanes of the fused pass store together) then fall
+    // into different banks, and quads of 4 bins starting at a multiple of 4 stay contiguous for the mel loads
+    // (layout chosen with tools/bank_sim.py: stores conflict free, mel gathers at 1.1x the minimum).
+    static SEPT_HD int bin_pos(int k) { return k + (k >> 4); }
+    // fused pass 2 + split task of a lane in round r: pair p = 2r + lane/16, row pair j = lane%16 (idle when j >= 13)
+    static SEPT_HD bool ps_task(int lane, int r, int& p, int& j) {
+        p = 2 * r + (lane >> 4);
+        j = lane & 15;
+        return j < 13 && p < PPW;
+    }
     static SEPT_HD int stage_floats(int hop) { return (LEAD + span(hop) + 1 + 3) & ~3; }
 };
 
@@ -185,9 +192,9 @@ SEPT_HD void zero_tail(pk2* base) {
 // pv[k1] = 4|X|^2 at bin CRT(k1, 25-j).  Row 0 (j = 0) is its own partner: pu holds the whole row and pv[0] the
 // Nyquist bin. ------------------------------------------------------------------------------------------------------
 template <class G>
-SEPT_HD void pass2_split(int task, const pk4* Y, const f2* tws, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
+SEPT_HD void pass2_split(int p, int j, const pk4* Y, const f2* tws, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
     constexpr int R = G::R;
-    const int p = task / 13, j = task % 13, rb = (25 - j) % 25;
+    const int rb = (25 - j) % 25;
     const pk4* yu = Y + p * G::YP + j * G::YS;
     const pk4* yv = Y + p * G::YP + rb * G::YS;
     pk2 ur[R], ui[R], vr[R], vi[R];
@@ -208,9 +215,9 @@ SEPT_HD void pass2_split(int task, const pk4* Y, const f2* tws, pk2 (&pu)[G::R],
 }
 
 template <class G>
-SEPT_HD void pass2_split_store(int task, pk2* P, const pk2 (&pu)[G::R], const pk2 (&pv)[G::R]) {
+SEPT_HD void pass2_split_store(int p, int j, pk2* P, const pk2 (&pu)[G::R], const pk2 (&pv)[G::R]) {
     constexpr int R = G::R, NC = G::NC;
-    const int p = task / 13, j = task % 13, rb = (25 - j) % 25;
+    const int rb = (25 - j) % 25;
     pk2* base = P + p * G::PP;
     const int kj = (Pfa<R>::cK2 * j) % NC, kb = (Pfa<R>::cK2 * rb) % NC;
 #pragma unroll
@@ -264,12 +271,12 @@ SEPT_HD void mel_band(const pk2* P, const f4* w4, band_t info, pk2 (&acc)[G::PPW
         const f4 w = w4[info.w4 + q];
 #pragma unroll
         for (int p = 0; p < G::PPW; ++p) {
-            const pk4* src = reinterpret_cast<const pk4*>(P + p * G::PP + G::bin_pos(info.k0 + 4 * q));
-            const pk4 a = src[0], b = src[1];
-            acc[p] = fma2(a.re, splat(w.x), acc[p]);
-            acc[p] = fma2(a.im, splat(w.y), acc[p]);
-            acc[p] = fma2(b.re, splat(w.z), acc[p]);
-            acc[p] = fma2(b.im, splat(w.w), acc[p]);
+            const pk2* src = P + p * G::PP + G::bin_pos(info.k0 + 4 * q);    // a quad never straddles a 16-bin block
+            const pk2 b0 = src[0], b1 = src[1], b2 = src[2], b3 = src[3];
+            acc[p] = fma2(b0, splat(w.x), acc[p]);
+            acc[p] = fma2(b1, splat(w.y), acc[p]);
+            acc[p] = fma2(b2, splat(w.z), acc[p]);
+            acc[p] = fma2(b3, splat(w.w), acc[p]);
         }
     }
 }

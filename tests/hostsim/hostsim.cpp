@@ -38,9 +38,14 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
         }
         const f2* tw2 = reinterpret_cast<const f2*>(tws.data());
         if constexpr (R <= 16) {
-            static pk2 pu[G::PS_TASKS][R], pv[G::PS_TASKS][R];
-            for (int task = 0; task < G::PS_TASKS; ++task) pass2_split<G>(task, Y.data(), tw2, pu[task], pv[task]);
-            for (int task = 0; task < G::PS_TASKS; ++task) pass2_split_store<G>(task, P, pu[task], pv[task]);
+            static pk2 pu[G::PS_ROUNDS][32][R], pv[G::PS_ROUNDS][32][R];
+            int p, j;
+            for (int r = 0; r < G::PS_ROUNDS; ++r)
+                for (int lane = 0; lane < 32; ++lane)
+                    if (G::ps_task(lane, r, p, j)) pass2_split<G>(p, j, Y.data(), tw2, pu[r][lane], pv[r][lane]);
+            for (int r = 0; r < G::PS_ROUNDS; ++r)
+                for (int lane = 0; lane < 32; ++lane)
+                    if (G::ps_task(lane, r, p, j)) pass2_split_store<G>(p, j, P, pu[r][lane], pv[r][lane]);
         } else {
             for (int task = 0; task < G::P2_TASKS; ++task) pass2_row<G>(task, Y.data());
             pk2 a[32][13], b[32][13];
