@@ -190,6 +190,12 @@ def workload_config(world: int, note: str | None = None):
 # B200 arm
 # --------------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    global N_FFT, HOP, FLOP_PER_FRAME, BYTES_PER_FRAME
+    if args.n_fft != N_FFT:
+        N_FFT = args.n_fft
+        HOP = 200 if N_FFT == 400 else 160
+        FLOP_PER_FRAME = {400: 20931 - 2 * 128 * 40 - 128, 1600: 49868}.get(N_FFT, FLOP_PER_FRAME)
+        BYTES_PER_FRAME = 4 * HOP + 4 * N_MELS
     import torch.distributed as dist
     from speech_emotion_privacy_trust_b200 import _lib, extraction
 
@@ -343,6 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary metric, e2e and cpu_baseline (profiling runs)")
+    ap.add_argument("--n-fft", type=int, default=N_FFT, help="debug only: time another FFT size (the metric is quoted on 800)")
     ap.add_argument("--utts", type=int, default=CORPUS_UTTS, help="utterances per GPU (debug only; the metric is quoted on the default)")
     args = ap.parse_args()
     if args.impl == "reference":

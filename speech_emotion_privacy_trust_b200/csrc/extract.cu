@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractPara
     const int warp_bytes = stage_floats * 4 + G::Y_PK4 * 16;
     unsigned char* wbase = smem_raw + const_bytes + warp * warp_bytes;
     float* stage = reinterpret_cast<float*>(wbase);
-    pk4* Y = reinterpret_cast<pk4*>(wbase + stage_floats * 4);
-    pk2* P = reinterpret_cast<pk2*>(Y);
+    pk2* Y = reinterpret_cast<pk2*>(wbase + stage_floats * 4);
+    pk2* P = Y;
 
     // ---- this CTA's contiguous item range; warps interleave inside it --------------------------------------
     const int n_items = __ldg(prm.item_off + prm.n_utts);
@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractPara
             float vmax = 0.f;
             for (int m = lane; m < n_mels; m += 32) {
                 pk2 acc[G::PPW];
-                mel_band<G>(P, melw, bands[m], acc);
+                const band_t info = bands[m];
+                mel_band<G>(P, melw, info, __shfl_sync(0xffffffffu, info.nq, 0), acc);
 #pragma unroll
                 for (int p = 0; p < G::PPW; ++p) {
                     const int ta = cur.t0 + 2 * p;
@@ -281,10 +282,12 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
 // ---- host launchers ----------------------------------------------------------------------------------------
 constexpr size_t kMaxSmem = 232448;      // 227 KB opt-in limit per CTA
 
-// tuning knob (bench experiments only): SEPT_EXTRACT_WARPS=8 selects the 8-warp / 255-register build of the kernel
-static int warp_cap(int r_default) {
+// tuning knob (bench experiments only): SEPT_EXTRACT_WARPS overrides the default warp count (<= 8 selects the
+// 255-register build of the kernel, more the 168-register one)
+static int warp_cap(int r_default, int r_max) {
     static const int env = [] { const char* e = getenv("SEPT_EXTRACT_WARPS"); return e ? atoi(e) : 0; }();
-    return (env > 0 && env < r_default) ? env : r_default;
+    const int w = env > 0 ? env : r_default;
+    return w < r_max ? w : r_max;
 }
 
 template <int R>
@@ -293,7 +296,7 @@ static int extract_warps(int hop, int n_wquads, int n_mels) {     // warps whose
     const size_t cb = (size_t)extract_const_bytes(R, n_wquads, n_mels), wb = G::stage_floats(hop) * 4 + G::Y_PK4 * 16;
     if (cb + wb > kMaxSmem) return 0;
     const int fit = (int)((kMaxSmem - cb) / wb);
-    const int cap = warp_cap(ExtractWarps<R>::value);
+    const int cap = warp_cap(ExtractWarpsDefault<R>::value, ExtractWarps<R>::value);
     return fit < cap ? fit : cap;
 }
 

@@ -14,7 +14,9 @@ enum : int {
 };
 
 // warps per CTA (one persistent CTA per SM); bounded by the 227 KB of shared memory the warp tiles take
-template <int R> struct ExtractWarps { static constexpr int value = (R == 16) ? 11 : 10; };   // upper bound; the launch fits fewer if hop is large
+template <int R> struct ExtractWarps { static constexpr int value = (R == 16) ? 11 : 10; };   // upper bound of the many-warp build
+// default warps per CTA: the fused pass-2 + split of R <= 16 wants ~200 registers, so 8 warps (255 registers) beat 11 (168 + spills)
+template <int R> struct ExtractWarpsDefault { static constexpr int value = 8; };
 
 struct ExtractParams {
     const float* wav;            // all utterances back to back

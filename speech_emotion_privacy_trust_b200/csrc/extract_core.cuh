@@ -13,7 +13,9 @@
 // Warp-private shared memory:
 //   stage  float [2 + SPAN + 1], SPAN = (FPW-1)*hop + n_fft   reflect-padded waveform span of the item at offset 2,
 //                                                one halo sample either side (for the waveform-gradient stream)
-//   Y      pk4   [PPW][25 rows k2][YS = R+1]     pass 1 output / pass 2 in place; (re, im) x (frame a, frame b)
+//   Y      pk2   [PPW][25 rows k2][re: R | im: R | pad 2]   pass 1 output / pass 2 input; each pk2 = (frame a, frame b).
+//                                                Real and imaginary parts sit in separate half rows so that their
+//                                                8-byte stores cannot be fused into quads (which costs 4 MOVs each)
 //   P      pk2   [PPW][PP] over the Y tile       4|X[k]|^2 of the frame pair at bin_pos(k) (written only after every Z
 //                                                of the item has been read into registers)
 // Replaces, for one item: torch.stft framing/window/rFFT + abs().pow(2) (torchaudio functional.py:123-144)
@@ -33,15 +35,16 @@ struct Geo {
     static constexpr int NC = R * 25, NFFT = 2 * NC, PAD = NFFT / 2;
     static constexpr int PPW = 32 / R;                           // packed frame pairs per warp
     static constexpr int FPW = 2 * PPW;                           // frames per item
-    static constexpr int YS = R + 1;                              // pk4 per k2 row (odd: rows hit distinct bank groups)
-    static constexpr int YP = 25 * YS + 2;                        // pk4 per pair
-    static constexpr int Y_PK4 = PPW * YP;                        // pk4 per warp
+    static constexpr int RS = 2 * R + 2;                          // pk2 per k2 row: [re: R][im: R][pad 2]; RS/2 odd spreads rows over banks
+    static constexpr int YP = 25 * RS + 4;                        // pk2 per pair
+    static constexpr int Y_PK2 = PPW * YP;                        // pk2 per warp
+    static constexpr int Y_PK4 = Y_PK2 / 2;                       // the same in 16-byte units
     static constexpr int PP = (NC + NC / 16 + 12) & ~1;           // pk2 per pair of the power tile (bins 0..NC+3, see bin_pos)
     static constexpr int TWS = R + 1;                             // f2 per split-twiddle row (odd: rows spread over banks)
     static constexpr int PS_ROUNDS = (PPW + 1) / 2;               // fused pass-2 + split: lane = (pair p % 2, row pair j < 13)
     static constexpr int P2_TASKS = PPW * 25;                     // pass-2 row tasks per item
     static constexpr int LEAD = 2;                                // floats in front of the staged span (halo + 8-byte alignment)
-    static_assert(PPW * PP <= 2 * Y_PK4, "power tile must fit in the Y tile it overwrites");
+    static_assert(PPW * PP <= Y_PK2, "power tile must fit in the Y tile it overwrites");
     static SEPT_HD int span(int hop) { return (FPW - 1) * hop + NFFT; }
     // pk2 slot of bin k in a pair's power tile: natural order with one 8-byte gap after every 16 bins.  Bins with
     // equal k mod 16 (the same k1 of different rows j, which the lanes of the fused pass store together) then fall
@@ -110,7 +113,7 @@ SEPT_HD bool item_is_interior(int n, int t0, int hop) {
 // (audio_feature_extraction.py:20): the central difference (x[j+1] - x[j-1]) / 2 is taken on the fly from the
 // neighbouring sample pairs, the 1/2 riding on the window (exact: a power of two).
 template <class G, bool DIFF>
-SEPT_HD void pass1(int lane, const float* stage, int hop, const f2* win2, pk4* Y) {
+SEPT_HD void pass1(int lane, const float* stage, int hop, const f2* win2, pk2* Y) {
     constexpr int R = G::R;
     const int p = lane / R, n1 = lane % R;
     const f2* xa = reinterpret_cast<const f2*>(stage + G::LEAD + (2 * p) * hop);
@@ -133,24 +136,34 @@ SEPT_HD void pass1(int lane, const float* stage, int hop, const f2* win2, pk4* Y
         }
     }
     Dft<25>::run(re, im);
-    pk2* y = reinterpret_cast<pk2*>(Y + p * G::YP + n1);           // two 8-byte stores: no register shuffling into quads
+    pk2* y = Y + p * G::YP + n1;
 #pragma unroll
-    for (int k2 = 0; k2 < 25; ++k2) { y[k2 * (2 * G::YS)] = re[k2]; y[k2 * (2 * G::YS) + 1] = im[k2]; }
+    for (int k2 = 0; k2 < 25; ++k2) { y[k2 * G::RS] = re[k2]; y[k2 * G::RS + R] = im[k2]; }
 }
 
-// ---- pass 2: row task (p, k2) transforms its R samples over n1, in place ----------------------------------------
+// load one k2 row (R complex samples of a frame pair) with 16-byte loads of two neighbouring real / imaginary parts
+template <int R>
+SEPT_HD void load_row(const pk2* y, pk2 (&re)[R], pk2 (&im)[R]) {
+#pragma unroll
+    for (int i = 0; i < R; i += 2) {
+        const pk4 a = *reinterpret_cast<const pk4*>(y + i);
+        const pk4 b = *reinterpret_cast<const pk4*>(y + R + i);
+        re[i] = a.re; re[i + 1] = a.im;                          // pk4's two halves: elements i and i+1
+        im[i] = b.re; im[i + 1] = b.im;
+    }
+}
+
+// ---- pass 2 (unfused form, R = 32): row task (p, k2) transforms its R samples over n1, in place ----------------
 template <class G>
-SEPT_HD void pass2_row(int task, pk4* Y) {
+SEPT_HD void pass2_row(int task, pk2* Y) {
     constexpr int R = G::R;
     const int p = task / 25, k2 = task % 25;
-    pk4* y = Y + p * G::YP + k2 * G::YS;
+    pk2* y = Y + p * G::YP + k2 * G::RS;
     pk2 re[R], im[R];
-#pragma unroll
-    for (int i = 0; i < R; ++i) { const pk4 v = y[i]; re[i] = v.re; im[i] = v.im; }
+    load_row<R>(y, re, im);
     Dft<R>::run(re, im);
-    pk2* y2 = reinterpret_cast<pk2*>(y);
 #pragma unroll
-    for (int i = 0; i < R; ++i) { y2[2 * i] = re[i]; y2[2 * i + 1] = im[i]; }
+    for (int i = 0; i < R; ++i) { y[i] = re[i]; y[R + i] = im[i]; }
 }
 
 // ---- real split of one conjugate pair: Zk = Z[k], Zm = Z[NC-k], tw = W_{NFFT}^k.  Returns 4|X[k]|^2 and
@@ -168,13 +181,14 @@ SEPT_HD void split_pair(pk4 zk, pk4 zm, pk2 twr, pk2 twi, pk2& pk_, pk2& pm_) {
 // iteration k2 (0..12) of the split: lane (p, k1) pairs Z at (k1, k2) with Z at (R-k1, 25-k2).
 // Returns false when the lane has nothing to do (row 0 is its own partner: only k1 <= R/2 work).
 template <class G>
-SEPT_HD bool split_load(int lane, int k2, const pk4* Y, const f2* tws, pk2& pk_, pk2& pm_) {
+SEPT_HD bool split_load(int lane, int k2, const pk2* Y, const f2* tws, pk2& pk_, pk2& pm_) {
     constexpr int R = G::R;
     const int p = lane / R, k1 = lane % R, km = (R - k1) % R;
     if (k2 == 0 && k1 > R / 2) return false;
     const int rb = (25 - k2) % 25;
-    const pk4 zk = Y[p * G::YP + k2 * G::YS + k1];
-    const pk4 zm = Y[p * G::YP + rb * G::YS + km];
+    const pk2* yk = Y + p * G::YP + k2 * G::RS + k1;
+    const pk2* ym = Y + p * G::YP + rb * G::RS + km;
+    const pk4 zk{yk[0], yk[R]}, zm{ym[0], ym[R]};
     const f2 tw = tws[k2 * G::TWS + k1];
     split_pair(zk, zm, splat(tw.x), splat(tw.y), pk_, pm_);
     return true;
@@ -192,16 +206,12 @@ SEPT_HD void zero_tail(pk2* base) {
 // pv[k1] = 4|X|^2 at bin CRT(k1, 25-j).  Row 0 (j = 0) is its own partner: pu holds the whole row and pv[0] the
 // Nyquist bin. ------------------------------------------------------------------------------------------------------
 template <class G>
-SEPT_HD void pass2_split(int p, int j, const pk4* Y, const f2* tws, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
+SEPT_HD void pass2_split(int p, int j, const pk2* Y, const f2* tws, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
     constexpr int R = G::R;
     const int rb = (25 - j) % 25;
-    const pk4* yu = Y + p * G::YP + j * G::YS;
-    const pk4* yv = Y + p * G::YP + rb * G::YS;
     pk2 ur[R], ui[R], vr[R], vi[R];
-#pragma unroll
-    for (int i = 0; i < R; ++i) { const pk4 a = yu[i]; ur[i] = a.re; ui[i] = a.im; }
-#pragma unroll
-    for (int i = 0; i < R; ++i) { const pk4 a = yv[i]; vr[i] = a.re; vi[i] = a.im; }
+    load_row<R>(Y + p * G::YP + j * G::RS, ur, ui);
+    load_row<R>(Y + p * G::YP + rb * G::RS, vr, vi);
     Dft<R>::run(ur, ui);
     Dft<R>::run(vr, vi);
     const f2* tw = tws + j * G::TWS;
@@ -263,11 +273,14 @@ SEPT_HD void split_store_all(int lane, pk2* P, const pk2 (&a)[13], const pk2 (&b
 // to whole quads that stay inside bins 0..NC+1 ------------------------------------------------------------------------
 struct alignas(16) band_t { int k0, w4, nq, pad; };
 
+// nq is the quad count of the widest band of the lane's round (uniform over the warp: no divergence); narrower bands
+// carry zero-weight quads up to it (tables.h pads them)
 template <class G>
-SEPT_HD void mel_band(const pk2* P, const f4* w4, band_t info, pk2 (&acc)[G::PPW]) {
+SEPT_HD void mel_band(const pk2* P, const f4* w4, band_t info, int nq, pk2 (&acc)[G::PPW]) {
 #pragma unroll
     for (int p = 0; p < G::PPW; ++p) acc[p] = splat(0.f);
-    for (int q = 0; q < info.nq; ++q) {
+#pragma unroll 2
+    for (int q = 0; q < nq; ++q) {
         const f4 w = w4[info.w4 + q];
 #pragma unroll
         for (int p = 0; p < G::PPW; ++p) {

@@ -58,24 +58,27 @@ inline void make_mel_bands(int n_fft, int n_mels, int sample_rate, std::vector<M
     std::vector<float> fb = make_mel_fbank(n_freqs, n_mels, sample_rate, 0.0, (double)(sample_rate / 2));
     bands.assign(n_mels, MelBand{0, 0, 0, 0});
     weights.clear();
-    for (int m = 0; m < n_mels; ++m) {
-        int lo = -1, hi = -1;
+    std::vector<int> lo(n_mels, -1), hi(n_mels, -1);
+    for (int m = 0; m < n_mels; ++m)
         for (int k = 0; k < n_freqs; ++k)
-            if (fb[(size_t)k * n_mels + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
-        MelBand b{0, (int32_t)(weights.size() / 4), 0, 0};
-        if (lo >= 0) {
-            const int k0 = lo & ~3;                                      // quads never straddle the tile's 16-bin blocks
-            const int nq = (hi - k0 + 4) / 4;                            // last bin read: k0 + 4*nq - 1 <= Nc + 3
-            b.k0 = k0;
-            b.nq = nq;
-            for (int i = 0; i < 4 * nq; ++i) {
+            if (fb[(size_t)k * n_mels + m] != 0.f) { if (lo[m] < 0) lo[m] = k; hi[m] = k; }
+    // the kernel gives band m to lane m % 32 in round m / 32 and runs every lane of a round for the round's widest band:
+    // narrower bands are padded with zero-weight quads (their reads must stay inside bins 0 .. Nc + 3)
+    for (int r0 = 0; r0 < n_mels; r0 += 32) {
+        int round_nq = 1;
+        for (int m = r0; m < n_mels && m < r0 + 32; ++m)
+            if (lo[m] >= 0) { const int nq = (hi[m] - (lo[m] & ~3) + 4) / 4; if (nq > round_nq) round_nq = nq; }
+        for (int m = r0; m < n_mels && m < r0 + 32; ++m) {
+            int k0 = lo[m] >= 0 ? (lo[m] & ~3) : 0;                  // quads never straddle the tile's 16-bin blocks
+            if (k0 + 4 * round_nq > Nc + 4) k0 = Nc + 4 - 4 * round_nq;
+            MelBand b{k0, (int32_t)(weights.size() / 4), round_nq, 0};
+            for (int i = 0; i < 4 * round_nq; ++i) {
                 const int k = k0 + i;
                 weights.push_back(k < n_freqs ? fb[(size_t)k * n_mels + m] * 0.25f : 0.f);
             }
+            bands[m] = b;
         }
-        bands[m] = b;
     }
-    while (weights.size() % 4) weights.push_back(0.f);
 }
 
 // split twiddles W_{n_fft}^{k}, k = CRT(k1, k2) for rows k2 = 0..12, columns k1 = 0..R-1: (cos, -sin) pairs, row

@@ -22,8 +22,9 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
     std::vector<float> weights;
     make_mel_bands(n_fft, n_mels, 16000, bands, weights);
     std::vector<float> stage(G::stage_floats(hop), 0.f);
-    std::vector<pk4> Y(G::Y_PK4);
-    pk2* P = reinterpret_cast<pk2*>(Y.data());
+    std::vector<pk4> Ybuf(G::Y_PK4 + 1);
+    pk2* Yp = reinterpret_cast<pk2*>(Ybuf.data());
+    pk2* P = Yp;
     std::vector<float> out((size_t)T * n_mels);
     const f2* win2 = reinterpret_cast<const f2*>(win.data());
     for (int t0 = 0; t0 < T; t0 += G::FPW) {
@@ -33,8 +34,8 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
         for (int lane = 0; lane < 32; ++lane)
             stage_item<G>(lane, wav.data(), n, t0, hop, interior ? 0 : deriv, stage.data());
         for (int lane = 0; lane < 32; ++lane) {
-            if (interior && deriv) pass1<G, true>(lane, stage.data(), hop, win2, Y.data());
-            else pass1<G, false>(lane, stage.data(), hop, win2, Y.data());
+            if (interior && deriv) pass1<G, true>(lane, stage.data(), hop, win2, Yp);
+            else pass1<G, false>(lane, stage.data(), hop, win2, Yp);
         }
         const f2* tw2 = reinterpret_cast<const f2*>(tws.data());
         if constexpr (R <= 16) {
@@ -42,17 +43,17 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
             int p, j;
             for (int r = 0; r < G::PS_ROUNDS; ++r)
                 for (int lane = 0; lane < 32; ++lane)
-                    if (G::ps_task(lane, r, p, j)) pass2_split<G>(p, j, Y.data(), tw2, pu[r][lane], pv[r][lane]);
+                    if (G::ps_task(lane, r, p, j)) pass2_split<G>(p, j, Yp, tw2, pu[r][lane], pv[r][lane]);
             for (int r = 0; r < G::PS_ROUNDS; ++r)
                 for (int lane = 0; lane < 32; ++lane)
                     if (G::ps_task(lane, r, p, j)) pass2_split_store<G>(p, j, P, pu[r][lane], pv[r][lane]);
         } else {
-            for (int task = 0; task < G::P2_TASKS; ++task) pass2_row<G>(task, Y.data());
+            for (int task = 0; task < G::P2_TASKS; ++task) pass2_row<G>(task, Yp);
             pk2 a[32][13], b[32][13];
             bool on0[32];
             for (int lane = 0; lane < 32; ++lane)
                 for (int k2 = 0; k2 <= 12; ++k2) {
-                    const bool on = split_load<G>(lane, k2, Y.data(), tw2, a[lane][k2], b[lane][k2]);
+                    const bool on = split_load<G>(lane, k2, Yp, tw2, a[lane][k2], b[lane][k2]);
                     if (k2 == 0) on0[lane] = on;
                 }
             for (int lane = 0; lane < 32; ++lane) split_store_all<G>(lane, P, a[lane], b[lane], on0[lane]);
@@ -60,7 +61,7 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
         for (int m = 0; m < n_mels; ++m) {
             pk2 acc[G::PPW];
             band_t info{bands[m].k0, bands[m].w4, bands[m].nq, 0};
-            mel_band<G>(P, reinterpret_cast<const f4*>(weights.data()), info, acc);
+            mel_band<G>(P, reinterpret_cast<const f4*>(weights.data()), info, info.nq, acc);
             for (int p = 0; p < G::PPW; ++p) {
                 const int ta = t0 + 2 * p;
                 if (ta < T) out[(size_t)ta * n_mels + m] = 10.0f * std::log10(std::fmax(lo(acc[p]), 1e-10f));
