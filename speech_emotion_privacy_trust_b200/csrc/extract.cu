@@ -177,13 +177,15 @@ __global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractPara
 
             // ---- mel bands (lane = band, all frame pairs of the item) + log + store --------------------------
             float vmax = 0.f;
-            for (int m = lane; m < n_mels; m += 32) {
+            for (int m0 = 0; m0 < n_mels; m0 += 32) {            // uniform over the warp: every lane runs every round
+                const int m = m0 + lane < n_mels ? m0 + lane : n_mels - 1;
+                const bool live = m0 + lane < n_mels;
                 pk2 acc[G::PPW];
                 const band_t info = bands[m];
                 mel_band<G>(P, melw, info, __shfl_sync(0xffffffffu, info.nq, 0), acc);
 #pragma unroll
                 for (int p = 0; p < G::PPW; ++p) {
-                    const int ta = cur.t0 + 2 * p;
+                    const int ta = live ? cur.t0 + 2 * p : cur.T;   // lanes past the last band store nothing
                     const float va = lo(acc[p]), vb = hi(acc[p]);
                     if (MODE == kModeDbFrameMajor) {
                         float* o = prm.out + (cur.f0 + ta) * n_mels + m;
