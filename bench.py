@@ -265,7 +265,7 @@ def run_b200(args):
         extras = {"skipped": True}
     elif rank == 0 or world > 1:
         try:
-            extras = secondary_metrics(args, dev, rank, world)
+            extras = secondary_metrics(args, dev, rank, world, batch if rank == 0 else None, hours)
         except Exception as exc:                                   # the headline number must not depend on the extras
             extras = {"error": f"{type(exc).__name__}: {exc}"}
 
@@ -336,10 +336,53 @@ def cpu_baseline():
                       "(one utterance per call, transforms built per call), best of 2"}
 
 
-def secondary_metrics(args, dev, rank, world):
-    """BASELINE.json's second figure: cloak+GRL training utterances/sec (config 3), data parallel, B=32 per GPU."""
+def secondary_metrics(args, dev, rank, world, batch=None, hours=None):
+    """BASELINE.json's second figure: cloak+GRL training utterances/sec (config 3), data parallel, B=32 per GPU; plus the
+    other features the reference's extraction script computes per utterance (this rank's numbers, device resident)."""
     from benchmarks_train import train_throughput
-    return train_throughput(dev, rank, world, steps=20, warmup=5)
+    out = train_throughput(dev, rank, world, steps=20, warmup=5)
+    if batch is not None:
+        out["other_features_this_rank"] = other_features(batch, hours, dev)
+    return out
+
+
+def other_features(batch, hours, dev, steps=5):
+    """audio-hours/s of log-mel n_fft=1600 (mel2), MFCC-40 x3 streams, and all three features of
+    audio_feature_extraction.py:185-187 back to back, with their FP32 roofline fractions."""
+    from speech_emotion_privacy_trust_b200 import extraction
+    peaks, _ = measured_peaks()
+    fp32_peak = torch.cuda.get_device_properties(dev).multi_processor_count * FP32_LANES_PER_SM * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps
+
+    f800 = batch.layout(800, 160).total_frames
+    f400 = batch.layout(400, 200).total_frames
+    mel_out = torch.empty((f800, N_MELS), dtype=torch.float32, device=dev)
+    mfcc_out = torch.empty(f400 * 120, dtype=torch.float32, device=dev)
+    res = {}
+    ms = timed(lambda: extraction.logmel(batch, n_fft=1600, n_mels=N_MELS, hop=160, out=mel_out))
+    res["logmel_1600"] = {"audio_hours_per_s": hours / (ms * 1e-3), "ms": ms, "fp32_frac": 49868 * f800 / (ms * 1e-3) / fp32_peak}
+    ms = timed(lambda: extraction.mfcc(batch, out=mfcc_out))
+    res["mfcc_3streams"] = {"audio_hours_per_s": hours / (ms * 1e-3), "ms": ms, "fp32_frac": 3 * 20931 * f400 / (ms * 1e-3) / fp32_peak}
+
+    def all_three():
+        extraction.logmel(batch, n_fft=800, n_mels=N_MELS, hop=160, out=mel_out)
+        extraction.logmel(batch, n_fft=1600, n_mels=N_MELS, hop=160, out=mel_out)
+        extraction.mfcc(batch, out=mfcc_out)
+    ms = timed(all_three)
+    flop = (22999 + 49868) * f800 + 3 * 20931 * f400
+    res["all_three"] = {"audio_hours_per_s": hours / (ms * 1e-3), "ms": ms, "fp32_frac": flop / (ms * 1e-3) / fp32_peak}
+    return res
 
 
 def main():
