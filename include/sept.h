@@ -71,7 +71,8 @@ int sept_logmel_f32(const float* wav_dev, const int64_t* utt_off_dev, const int6
  * (feature_extraction/audio_feature_extraction.py:15-26 -> torchaudio/transforms/_transforms.py:634-718): n_fft 400,
  * hop 200, 128 mels, dB with top_db = 80 below the per-utterance maximum, orthonormal DCT-II.
  * Layouts must come from sept_extract_layout(n_fft=400, hop=200).
- * scratch_dev: 2 * total_frames * 128 floats; utt_max_dev: 2 * n_utts int32 (the call zeroes it);
+ * scratch_dev: total_frames * 257 floats (two mel-power streams + a frame->utterance map); utt_max_dev: 2 * n_utts
+ * int32 (the call zeroes it);
  * out_dev: total_frames * 120 floats, utterance u is a (120, T_u) block at frame_off[u] * 120. */
 int sept_mfcc_f32(const float* wav_dev, const int64_t* utt_off_dev, const int64_t* frame_off_dev,
                   const int32_t* item_off_dev, int n_utts, int64_t total_frames, float* scratch_dev,

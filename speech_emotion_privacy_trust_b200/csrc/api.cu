@@ -211,9 +211,10 @@ int sept_mfcc_f32(const float* wav, const int64_t* utt_off, const int64_t* frame
     p.n_utts = n_utts; p.hop = 200; p.n_mels = 128; p.n_wquads = c.n_wquads; p.total_frames = total_frames;
     p.window = c.window; p.tws = c.tws; p.mel_w = c.mel_w; p.mel_bands = c.mel_bands;
     p.out = scratch; p.utt_max = utt_max;
+    p.frame_utt = reinterpret_cast<int*>(scratch + 2 * (size_t)total_frames * 128);
     SEPT_CUDA(sept::launch_extract(p, 400, sept::kModeMfccPower, sms, st));
     sept::MfccDctParams d{};
-    d.power = scratch; d.utt_max = utt_max; d.frame_off = frame_off; d.dct = dct; d.n_utts = n_utts;
+    d.power = scratch; d.utt_max = utt_max; d.frame_utt = p.frame_utt; d.frame_off = frame_off; d.dct = dct; d.n_utts = n_utts;
     d.total_frames = total_frames; d.top_db = 80.0f; d.out = out;
     SEPT_CUDA(sept::launch_mfcc_dct(d, st));
     return SEPT_OK;

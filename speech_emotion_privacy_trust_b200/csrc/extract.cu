@@ -203,6 +203,8 @@ __global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractPara
                 }
             }
             if (MODE == kModeMfccPower) {
+                if (stream == 0 && lane < G::FPW && cur.t0 + lane < cur.T)
+                    prm.frame_utt[cur.f0 + cur.t0 + lane] = cur.u;   // saves the DCT kernel a search per frame
                 // per-utterance max of the mel power (top_db floor, functional.py:393-402); non-negative floats
                 // order like their bit patterns
 #pragma unroll
@@ -216,61 +218,98 @@ __global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractPara
 }
 
 // ---- MFCC phase 2: dB with the per-utterance floor, then DCT (transforms/_transforms.py:714-717) ------------
-// One CTA handles kDctFrames consecutive global frames (they may straddle utterances).  Thread (f = tid % 32,
-// q = tid / 32) produces coefficients [10q, 10q+10) of the three streams of frame f.
+// One CTA handles kDctFrames consecutive global frames (they may straddle utterances).  The load phase converts the
+// two mel-power streams into the three clamped dB streams in shared memory (np.gradient(x, 2) == np.gradient(x) / 2
+// exactly, so stream 2 is the dB of a quarter of stream 1's power); then thread (f = tid % 32, q = tid / 32) produces
+// coefficients [10q, 10q+10) of the three streams of frame f: 30 accumulators, 3 + 3 shared loads per 30 FMAs.
 constexpr int kDctFrames = 32;
 constexpr int kDctThreads = 128;
+constexpr int kDctNM = 128, kDctNC = 40, kDctDS = 40, kDctXS = kDctNM + 1;
+constexpr size_t kDctSmem = (kDctNM * kDctDS + 3 * kDctFrames * kDctXS + 4 * kDctFrames) * 4;
 
 __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctParams prm) {
-    constexpr int NM = 128, NC = 40, DS = 44;                    // D row stride (floats), keeps float2 alignment
+    constexpr int NM = kDctNM, NC = kDctNC, DS = kDctDS, XS = kDctXS;
     extern __shared__ __align__(16) unsigned char dct_smem[];
     float* D = reinterpret_cast<float*>(dct_smem);                                   // [NM][DS]
-    float (*X)[kDctFrames][NM + 1] = reinterpret_cast<float (*)[kDctFrames][NM + 1]>(D + NM * DS);
-    int* frame_utt = reinterpret_cast<int*>(D + NM * DS + 2 * kDctFrames * (NM + 1));
+    float* X = D + NM * DS;                                                          // [3][kDctFrames][XS] clamped dB
+    int* frame_utt = reinterpret_cast<int*>(X + 3 * kDctFrames * XS);                // [kDctFrames]
+    float* frame_floor = reinterpret_cast<float*>(frame_utt + kDctFrames);           // [3][kDctFrames]
     const long long g0 = (long long)blockIdx.x * kDctFrames;
-    for (int i = threadIdx.x; i < NM * NC; i += kDctThreads) D[(i / NC) * DS + (i % NC)] = prm.dct[i];
-    for (int i = threadIdx.x; i < 2 * kDctFrames * NM; i += kDctThreads) {
-        const int s = i / (kDctFrames * NM), r = i % (kDctFrames * NM), f = r / NM, m = r % NM;
-        const long long g = g0 + f;
-        X[s][f][m] = g < prm.total_frames ? prm.power[((long long)s * prm.total_frames + g) * NM + m] : 0.f;
-    }
+    for (int i = threadIdx.x; i < NM * NC / 4; i += kDctThreads)
+        reinterpret_cast<float4*>(D)[i] = reinterpret_cast<const float4*>(prm.dct)[i];
     if (threadIdx.x < kDctFrames) {
         const long long g = g0 + threadIdx.x;
-        int lo_ = 0, hi_ = prm.n_utts - 1;
-        while (lo_ < hi_) {
-            const int mid = (lo_ + hi_) >> 1;
-            if (prm.frame_off[mid + 1] > g) hi_ = mid; else lo_ = mid + 1;
-        }
+        const int lo_ = g < prm.total_frames ? prm.frame_utt[g] : 0;
         frame_utt[threadIdx.x] = lo_;
+        const float max0 = __int_as_float(prm.utt_max[lo_]), max1 = __int_as_float(prm.utt_max[prm.n_utts + lo_]);
+        frame_floor[threadIdx.x] = power_to_db(max0) - prm.top_db;
+        frame_floor[kDctFrames + threadIdx.x] = power_to_db(max1) - prm.top_db;
+        frame_floor[2 * kDctFrames + threadIdx.x] = power_to_db(0.25f * max1) - prm.top_db;
+    }
+    // load phase: all 16 float4 loads of a thread are issued before the first is used; a warp covers 4 frames x 8
+    // quads per step (128-byte segments in HBM, and 32 distinct banks for its scalar stores into the 129-float rows)
+    {
+        constexpr int NIT = 2 * kDctFrames * (NM / 4) / kDctThreads;                 // 16
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int f_lo = lane >> 3, m4_lo = lane & 7;
+        float4 pw[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int combo = it * 4 + warp, s = combo >> 5, rem = combo & 31;
+            const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
+            const long long g = g0 + f;
+            pw[it] = g < prm.total_frames
+                         ? __ldg(reinterpret_cast<const float4*>(prm.power + ((long long)s * prm.total_frames + g) * NM) + m4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();                                                             // frame_floor is ready
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int combo = it * 4 + warp, s = combo >> 5, rem = combo & 31;
+            const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
+            const float v[4] = {pw[it].x, pw[it].y, pw[it].z, pw[it].w};
+            float* x = X + (s * kDctFrames + f) * XS + 4 * m4;
+            const float fl = frame_floor[s * kDctFrames + f];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) x[c] = fmaxf(power_to_db(v[c]), fl);
+            if (s == 1) {
+                float* x2 = X + (2 * kDctFrames + f) * XS + 4 * m4;
+                const float fl2 = frame_floor[2 * kDctFrames + f];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) x2[c] = fmaxf(power_to_db(0.25f * v[c]), fl2);
+            }
+        }
     }
     __syncthreads();
     const int f = threadIdx.x & 31, q = threadIdx.x >> 5;
     const long long g = g0 + f;
     if (g >= prm.total_frames) return;
-    const int u = frame_utt[f];
-    const float max0 = __int_as_float(prm.utt_max[u]), max1 = __int_as_float(prm.utt_max[prm.n_utts + u]);
-    const float floor0 = power_to_db(max0) - prm.top_db;
-    const float floor1 = power_to_db(max1) - prm.top_db;
-    const float floor2 = power_to_db(0.25f * max1) - prm.top_db;
     float acc[3][10];
 #pragma unroll
     for (int s = 0; s < 3; ++s)
 #pragma unroll
         for (int c = 0; c < 10; ++c) acc[s][c] = 0.f;
+    const float* x0 = X + f * XS;
+    const float* x1 = x0 + kDctFrames * XS;
+    const float* x2 = x1 + kDctFrames * XS;
+    const float* drow = D + 10 * q;
+#pragma unroll 4
     for (int m = 0; m < NM; ++m) {
-        const float p0 = X[0][f][m], p1 = X[1][f][m];
-        const float d0 = fmaxf(power_to_db(p0), floor0);
-        const float d1 = fmaxf(power_to_db(p1), floor1);
-        const float d2 = fmaxf(power_to_db(0.25f * p1), floor2);   // np.gradient(x, 2) == np.gradient(x) / 2 exactly
-        const float* drow = D + m * DS + 10 * q;
+        const float d0 = x0[m], d1 = x1[m], d2 = x2[m];
+        const float2 w01 = *reinterpret_cast<const float2*>(drow + m * DS);
+        const float2 w23 = *reinterpret_cast<const float2*>(drow + m * DS + 2);
+        const float2 w45 = *reinterpret_cast<const float2*>(drow + m * DS + 4);
+        const float2 w67 = *reinterpret_cast<const float2*>(drow + m * DS + 6);
+        const float2 w89 = *reinterpret_cast<const float2*>(drow + m * DS + 8);
+        const float w[10] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w89.x, w89.y};
 #pragma unroll
         for (int c = 0; c < 10; ++c) {
-            const float w = drow[c];
-            acc[0][c] = fmaf(d0, w, acc[0][c]);
-            acc[1][c] = fmaf(d1, w, acc[1][c]);
-            acc[2][c] = fmaf(d2, w, acc[2][c]);
+            acc[0][c] = fmaf(d0, w[c], acc[0][c]);
+            acc[1][c] = fmaf(d1, w[c], acc[1][c]);
+            acc[2][c] = fmaf(d2, w[c], acc[2][c]);
         }
     }
+    const int u = frame_utt[f];
     const long long f0 = prm.frame_off[u];
     const int T = (int)(prm.frame_off[u + 1] - f0);
     const int t = (int)(g - f0);
@@ -361,7 +400,7 @@ size_t extract_smem_bytes_for(int n_fft, int hop, int n_wquads, int n_mels) {
 cudaError_t launch_mfcc_dct(const MfccDctParams& prm, cudaStream_t stream) {
     const long long blocks = (prm.total_frames + kDctFrames - 1) / kDctFrames;
     if (blocks == 0) return cudaSuccess;
-    const size_t smem = (128 * 44 + 2 * kDctFrames * 129 + kDctFrames) * 4;
+    const size_t smem = kDctSmem;
     cudaError_t e = cudaFuncSetAttribute(mfcc_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mfcc_dct_kernel<<<(unsigned)blocks, kDctThreads, smem, stream>>>(prm);

@@ -35,11 +35,13 @@ struct ExtractParams {
     const void* mel_bands;       // [n_mels] {int k0, w4, nq, pad}
     float* out;
     int* utt_max;                // kModeMfccPower: [2][n_utts] float bits, zeroed by the caller
+    int* frame_utt;              // kModeMfccPower: [total_frames] utterance of every frame
 };
 
 struct MfccDctParams {
     const float* power;          // [2][total_frames][128] from kModeMfccPower
     const int* utt_max;          // [2][n_utts]
+    const int* frame_utt;        // [total_frames] from kModeMfccPower
     const int64_t* frame_off;    // [n_utts + 1]
     const float* dct;            // [128][40]
     int n_utts;

@@ -105,7 +105,7 @@ def mfcc(batch: RaggedAudio, out: torch.Tensor | None = None) -> tuple[torch.Ten
     tf = lay.total_frames
     if out is None:
         out = torch.empty(tf * 3 * N_MFCC, dtype=torch.float32, device=dev)
-    scratch = torch.empty(2 * tf * 128, dtype=torch.float32, device=dev)
+    scratch = torch.empty(tf * 257, dtype=torch.float32, device=dev)
     utt_max = torch.empty(2 * batch.n_utts, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().sept_mfcc_f32(batch.wav.data_ptr(), batch.utt_off.data_ptr(), lay.frame_off.data_ptr(),
