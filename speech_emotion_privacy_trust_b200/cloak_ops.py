@@ -37,8 +37,10 @@ def _alias(t: torch.Tensor) -> torch.Tensor:
     return torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage(), t.storage_offset(), t.size(), t.stride())
 
 
-def cloak_forward_raw(x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, want_noise=False):
-    """One launch of sept_cloak_fwd_f32.  Returns (out, eps_used, noise | None).  x may be None (noise only)."""
+def cloak_forward_raw(x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, want_noise=False, draw=None):
+    """One launch of sept_cloak_fwd_f32.  Returns (out, eps_used, noise | None).  x may be None (noise only).
+    draw: optional device int64 counter of draws so far; it selects the Philox offset on the device and is advanced by
+    one after the launch (CUDA-graph friendly: every replay draws a fresh eps)."""
     _lib.require_cuda(locs)
     wf = locs.numel()
     dev = locs.device
@@ -51,9 +53,12 @@ def cloak_forward_raw(x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().sept_cloak_fwd_f32(
             _ptr(x) if x is not None else locs.data_ptr(), locs.data_ptr(), rhos.data_ptr(), _ptr(mask), _ptr(eps),
-            int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset) & 0xFFFFFFFFFFFFFFFF, float(eps_std), float(min_scale), float(max_scale),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset) & 0xFFFFFFFFFFFFFFFF, _ptr(draw) if eps is None else 0, float(eps_std),
+            float(min_scale), float(max_scale),
             batch, wf, _ptr(out) if out is not None else locs.data_ptr(), eps_used.data_ptr() if eps is None else 0,
             _ptr(noise), _stream(dev)))
+        if draw is not None and eps is None:
+            _lib.check(_lib.lib().sept_counter_add_u64(draw.data_ptr(), 1, _stream(dev)))
     return out, eps_used, noise
 
 
@@ -65,13 +70,14 @@ class CloakNoiseFunction(torch.autograd.Function):
     the separate -lambda*g launch and autograd's gradient accumulation pass."""
 
     @staticmethod
-    def forward(ctx, x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, twin, grl_lambda):
+    def forward(ctx, x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, twin, grl_lambda, draw=None):
         _lib.require_cuda(x)
         x = _f32c(x)
         locs_c, rhos_c = _f32c(locs.detach()), _f32c(rhos.detach())
         mask_c = None if mask is None else _f32c(mask.detach().to(x.device))
         eps_c = None if eps is None else _f32c(eps.detach().to(x.device)).reshape(-1)
-        out, eps_used, _ = cloak_forward_raw(x, locs_c, rhos_c, mask_c, eps_c, seed, offset, eps_std, min_scale, max_scale)
+        out, eps_used, _ = cloak_forward_raw(x, locs_c, rhos_c, mask_c, eps_c, seed, offset, eps_std, min_scale, max_scale,
+                                             draw=draw)
         ctx.save_for_backward(eps_used, rhos_c, mask_c)
         ctx.cfg = (float(min_scale), float(max_scale), float(grl_lambda), bool(twin), tuple(locs.shape))
         if twin:
@@ -83,7 +89,7 @@ class CloakNoiseFunction(torch.autograd.Function):
         eps_used, rhos_c, mask_c = ctx.saved_tensors
         min_scale, max_scale, lam, twin, pshape = ctx.cfg
         if g_a is None and g_b is None:
-            return (None,) * 12
+            return (None,) * 13
         if g_a is None:
             g_a = torch.zeros_like(g_b)
         g_a = _f32c(g_a)
@@ -101,7 +107,7 @@ class CloakNoiseFunction(torch.autograd.Function):
                 g_a.data_ptr(), _ptr(g_b), lam, eps_used.data_ptr(), rhos_c.data_ptr(), _ptr(mask_c), min_scale, max_scale,
                 batch, wf, ws.data_ptr(), dlocs.data_ptr(), _ptr(drhos), _ptr(dx), _stream(dev)))
         return (dx, dlocs.view(pshape) if need_locs else None, drhos.view(pshape) if need_rhos else None,
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 class GradientReversalFunction(torch.autograd.Function):

@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(kCloakThreads) cloak_fwd_kernel(const CloakFwd
     if (i4 * 4 >= p.wf) return;
     const int i = i4 * 4;
     const float4 mu = ld4(p.locs + i), rho = ld4(p.rhos + i);
-    float4 e = p.eps ? ld4(p.eps + i) : normal4(p.seed, p.offset, (uint32_t)i4, p.eps_std);
+    const uint64_t off = p.draw_dev ? p.offset + *p.draw_dev * (uint64_t)((p.wf + 3) / 4) : p.offset;
+    float4 e = p.eps ? ld4(p.eps + i) : normal4(p.seed, off, (uint32_t)i4, p.eps_std);
     if (p.eps_out && blockIdx.y == 0) st4(p.eps_out + i, e);
     float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
     if (p.mask) {
@@ -148,6 +149,13 @@ __global__ void __launch_bounds__(256) grl_bwd_kernel(const float* __restrict__ 
             for (size_t j = i; j < n; ++j) dx[j] = neg_lambda * g[j];
         }
     }
+}
+
+__global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
+
+cudaError_t launch_counter_add(uint64_t* counter, uint64_t inc, cudaStream_t stream) {
+    counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+    return cudaGetLastError();
 }
 
 int cloak_slices(int batch) { return batch < kCloakSlices ? (batch > 0 ? batch : 1) : kCloakSlices; }

@@ -15,6 +15,7 @@ struct CloakFwdParams {
     const float* mask;       // (wf) or null
     const float* eps;        // (wf) or null -> Philox(seed, offset)
     uint64_t seed, offset;
+    const uint64_t* draw_dev; // null, or device counter: the Philox offset becomes offset + *draw_dev * ceil(wf / 4)
     float eps_std;           // 0.1 in the reference (cloak_models.py:37)
     float min_scale, max_scale;
     int batch, wf;
@@ -43,6 +44,7 @@ struct CloakBwdParams {
 int cloak_slices(int batch);
 cudaError_t launch_cloak_fwd(const CloakFwdParams& p, cudaStream_t stream);
 cudaError_t launch_cloak_bwd(const CloakBwdParams& p, cudaStream_t stream);
+cudaError_t launch_counter_add(uint64_t* counter, uint64_t inc, cudaStream_t stream);
 cudaError_t launch_grl_bwd(const float* g, float lambda, size_t n, float* dx, cudaStream_t stream);
 
 }  // namespace sept

@@ -26,28 +26,29 @@ class cloak_noise(nn.Module):
         self.device = device
         self.normal = torch.distributions.normal.Normal(0, EPS_STD)
         self.external_eps = None      # set to a (1, W, F) tensor to supply eps instead of drawing it on the device
-        self._draws = 0               # Philox offset: advances once per sample, identical on every data-parallel rank
+        self._draws = None            # device counter of samples drawn: the Philox offset lives on the GPU, so a captured
+                                      # CUDA graph draws a fresh eps per replay; identical on every data-parallel rank
 
     def scales(self):
         return (1.0 + torch.tanh(self.rhos)) / 2 * (self.max_scale - self.min_scale) + self.min_scale
 
     # ---- eps source -------------------------------------------------------------------------------------------
     def _eps_source(self):
-        """(eps | None, seed, offset).  eps is external when the caller set `external_eps` or replaced
+        """(eps | None, seed, draw counter).  eps is external when the caller set `external_eps` or replaced
         `self.normal.sample` (the reference's own hook for injecting a known sample, cloak_models.py:47)."""
         if self.external_eps is not None:
-            return self.external_eps, 0, 0
+            return self.external_eps, 0, None
         if 'sample' in vars(self.normal):
-            return self.normal.sample(self.rhos.shape), 0, 0
-        offset = self._draws * ((self.rhos.numel() + 3) // 4)
-        self._draws += 1
-        return None, torch.initial_seed(), offset
+            return self.normal.sample(self.rhos.shape), 0, None
+        if self._draws is None or self._draws.device != self.rhos.device:
+            self._draws = torch.zeros(1, dtype=torch.int64, device=self.rhos.device)
+        return None, torch.initial_seed(), self._draws
 
     def sample_noise(self, mask=None):
-        eps, seed, offset = self._eps_source()
+        eps, seed, draw = self._eps_source()
         if eps is None:
-            _, eps, _ = cloak_ops.cloak_forward_raw(None, self.locs.detach(), self.rhos.detach(), None, None, seed, offset,
-                                                    EPS_STD, self.min_scale, self.max_scale)
+            _, eps, _ = cloak_ops.cloak_forward_raw(None, self.locs.detach(), self.rhos.detach(), None, None, seed, 0,
+                                                    EPS_STD, self.min_scale, self.max_scale, draw=draw)
             eps = eps.view(self.rhos.shape)
         eps = eps.to(self.rhos.device)
         if mask is not None:
@@ -55,15 +56,15 @@ class cloak_noise(nn.Module):
         return self.locs + self.scales() * eps
 
     def forward(self, input, mask=None):
-        eps, seed, offset = self._eps_source()
-        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, offset, EPS_STD,
-                                                  self.min_scale, self.max_scale, False, 0.0)
+        eps, seed, draw = self._eps_source()
+        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, 0, EPS_STD,
+                                                  self.min_scale, self.max_scale, False, 0.0, draw)
 
     def forward_with_reversed_twin(self, input, mask, grl_lambda):
         """(y, y_rev): y_rev carries the same values and reverses its gradient by -grl_lambda inside the fused backward."""
-        eps, seed, offset = self._eps_source()
-        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, offset, EPS_STD,
-                                                  self.min_scale, self.max_scale, True, float(grl_lambda))
+        eps, seed, draw = self._eps_source()
+        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, 0, EPS_STD,
+                                                  self.min_scale, self.max_scale, True, float(grl_lambda), draw)
 
 
 def _freeze(model):

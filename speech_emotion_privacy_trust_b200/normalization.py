@@ -106,3 +106,29 @@ def normalized_windows(feat: torch.Tensor, lay: Layout, st: SpeakerStats, win_ut
             feat.data_ptr(), lay.frame_off.data_ptr(), st.spk_of_utt.data_ptr(), st.stats.data_ptr(), d_wu.data_ptr(),
             d_wt.data_ptr(), n, win_len, F, MODES[mode], out.data_ptr(), _stream(dev)))
     return out
+
+
+def speaker_stats_distributed(feat: torch.Tensor, lay: Layout, speaker_of_utt: Sequence, all_speakers: Sequence,
+                              whole_utterance: Sequence[bool] | None = None, group=None, win_len: int = WIN_LEN,
+                              shift_len: int = SHIFT_LEN) -> SpeakerStats:
+    """Per-speaker statistics when a speaker's utterances are spread over several ranks (they are under length-bucketed
+    sharding): every rank reduces its own utterances with the kernels, then ONE all-gather of the
+    (count, mean, M2, min, max) partials and a Chan merge in rank order give every rank the global statistics.
+    `all_speakers` fixes the row order on every rank (speakers a rank does not hold contribute empty partials)."""
+    from . import parallel
+    local = speaker_stats(feat, lay, speaker_of_utt, whole_utterance, win_len, shift_len)
+    dev, F = feat.device, feat.shape[1]
+    row = {s: i for i, s in enumerate(all_speakers)}
+    n_spk = len(all_speakers)
+    cnt = torch.zeros((n_spk, F), dtype=torch.float32, device=dev)
+    mean, m2 = torch.zeros_like(cnt), torch.zeros_like(cnt)
+    mn, mx = torch.full_like(cnt, float("inf")), torch.full_like(cnt, float("-inf"))
+    if local.speakers:
+        idx = torch.tensor([row[s] for s in local.speakers], device=dev)
+        st = local.stats
+        cnt[idx], mean[idx], m2[idx] = st[:, 0], st[:, 1], st[:, 2] * st[:, 2] * st[:, 0]
+        mn[idx], mx[idx] = st[:, 3], st[:, 4]
+    n, mu, sd, lo, hi = parallel.merge_speaker_partials(cnt, mean, m2, mn, mx, group=group)
+    stats = torch.stack([n, mu, sd, lo, hi], dim=1).contiguous()
+    spk_idx = torch.tensor([row[s] for s in speaker_of_utt], dtype=torch.int32, device=dev)
+    return SpeakerStats(list(all_speakers), stats, spk_idx)

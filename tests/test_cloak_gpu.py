@@ -165,3 +165,52 @@ def test_grl_model_matches_unfused_composition(mods):
         scale = max(1e-3, float(b[i].abs().max()))
         assert float((a[i] - b[i]).abs().max()) < 2e-3 * scale, name     # cuDNN conv/GRU (TF32-capable) sit in between
     assert all(p.grad is None for p in model.original_model.parameters())
+
+
+def test_cloak_inside_cuda_graph_draws_fresh_noise(mods):
+    """The Philox draw counter lives on the device: replaying a captured forward yields a new eps each time, and the
+    sequence equals the eager one for the same seed (what keeps data-parallel ranks in step)."""
+    cloak_models, _, _ = mods
+    x = torch.zeros(2, 1, 200, 128, device="cuda")
+
+    def fresh():
+        torch.manual_seed(11)
+        return cloak_models.cloak_noise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 10.0, "cuda").cuda()
+    eager = fresh()
+    want = [eager(x).clone() for _ in range(4)]
+    layer = fresh()
+    with torch.no_grad():
+        first = layer(x).clone()                          # warm-up (allocations) consumes draw 0
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = layer(x)
+        outs = []
+        for _ in range(3):
+            g.replay()
+            outs.append(y.clone())
+    assert torch.equal(first, want[0])
+    # capture itself does not execute kernels, so the replays are draws 1, 2, 3
+    for got, ref in zip(outs, want[1:]):
+        assert torch.equal(got, ref)
+    assert not torch.equal(outs[0], outs[1])
+
+
+def test_distributed_speaker_stats_single_rank_equals_local():
+    from speech_emotion_privacy_trust_b200 import normalization as nz
+    from speech_emotion_privacy_trust_b200.extraction import Layout
+    rng = np.random.default_rng(3)
+    frames = [230, 410, 199, 305]
+    spk = ["x", "y", "x", "z"]
+    feats = [(rng.standard_normal((T, 128)) * 4 - 20).astype(np.float32) for T in frames]
+    fo = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+    lay = Layout(fo, torch.from_numpy(fo).cuda(), torch.zeros(len(fo), dtype=torch.int32, device="cuda"))
+    feat = torch.from_numpy(np.concatenate(feats)).cuda()
+    a = nz.speaker_stats(feat, lay, spk)
+    b = nz.speaker_stats_distributed(feat, lay, spk, all_speakers=["z", "y", "x", "absent"])
+    da, db = a.as_dict(), b.as_dict()
+    for s in ("x", "y", "z"):
+        for k in ("count", "mean", "std", "min", "max"):
+            assert np.allclose(da[s][k], db[s][k], rtol=0, atol=2e-5), (s, k)
+    assert float(db["absent"]["count"][0]) == 0.0
+    za, zb = nz.normalize(feat, lay, a), nz.normalize(feat, lay, b)
+    assert float((za - zb).abs().max()) < 1e-4
