@@ -99,3 +99,38 @@ def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_la
             "model": "two_d_cnn_lstm_syn_with_grl(two_d_cnn_lstm h=64 x2)", "memory_format": "channels_last" if channels_last else "contiguous", "cuda_graphs": bool(graphs), "trainable_params": n_params,
             "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0, "final_loss": float(loss_host[0]),
             "h2d_bytes_per_step": int(batch * 200 * 128 * 4 + batch * 16), "includes": "H2D batch, fwd, bwd, all-reduce, SGD, loss D2H"}
+
+
+def eval_throughput(dev, n_utts=64, steps=5, seed=8):
+    """Config 2 / 5 of BASELINE.json: cloak evaluation (adversary_cloak_evaluation.test semantics) on 64 synthetic test
+    utterances of 2-10 s: sliding 200/50 windows, per-window noise, emotion classifier + gender adversary, softmax mean
+    and argmax per utterance; windows/s including the window gather/normalisation and the prediction read-back."""
+    from speech_emotion_privacy_trust_b200 import dropin, evaluation, normalization
+    from speech_emotion_privacy_trust_b200.extraction import Layout
+    dropin.install()
+    import baseline_models
+    import cloak_models
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    frames = rng.integers(201, 1002, size=n_utts)
+    fo = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+    lay = Layout(fo, torch.from_numpy(fo).to(dev), torch.zeros(len(fo), dtype=torch.int32, device=dev))
+    feat = (torch.randn((int(fo[-1]), 128), device=dev) * 8 - 40).contiguous()
+    st = normalization.speaker_stats(feat, lay, [u % 10 for u in range(n_utts)], whole_utterance=[True] * n_utts)
+    mk = lambda pred: baseline_models.two_d_cnn_lstm(1, 128, 5, lstm_hidden_size=64, pred=pred, global_feature=0).to(dev).eval()
+    base, adv = mk("emotion").to(memory_format=torch.channels_last), mk("gender").to(memory_format=torch.channels_last)
+    layer = cloak_models.cloak_noise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 5.0, dev).to(dev)
+    mask = evaluation.suppression_mask(layer, 0)
+    n_win = len(evaluation.eval_window_table(lay)[0])
+    for _ in range(2):
+        evaluation.cloak_evaluate(layer, base, adv, feat, lay, st, mask=mask)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        evaluation.cloak_evaluate(layer, base, adv, feat, lay, st, mask=mask)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "cloak evaluation windows/sec", "value": n_win / (ms * 1e-3), "unit": "windows/s", "utterances_per_s": n_utts / (ms * 1e-3),
+            "utterances": n_utts, "windows": n_win, "ms_per_pass": ms, "max_windows_per_forward": 512}

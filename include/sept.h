@@ -106,12 +106,14 @@ int sept_normalize_windows_f32(const float* feat_dev, const int64_t* frame_off_d
  * the noise sample; otherwise it is drawn on the device as eps_std * N(0,1) from Philox4x32-10(seed, offset) (the
  * reference draws Normal(0, 0.1) on the CPU, :37,47).  draw_dev (may be NULL) is a device counter of draws so far: the
  * Philox offset becomes offset + *draw_dev * ceil(wf/4), which lets a CUDA graph that contains this call produce a fresh
- * sample on every replay (advance it with sept_counter_add_u64 inside the same graph).  mask_dev, eps_out_dev,
- * noise_out_dev may be NULL.  wf = W*F must be a multiple of 4. */
+ * sample on every replay (advance it with sept_counter_add_u64 inside the same graph).  per_sample = 1 gives every batch
+ * element its own eps (eps_dev / eps_out_dev are then (batch, wf), draw index *draw_dev + b): the batched equivalent of
+ * the reference's evaluation loop that calls the layer once per window (training/adversary_cloak_evaluation.py:73-83);
+ * forward only.  mask_dev, eps_out_dev, noise_out_dev may be NULL.  wf = W*F must be a multiple of 4. */
 int sept_cloak_fwd_f32(const float* x_dev, const float* locs_dev, const float* rhos_dev, const float* mask_dev,
-                       const float* eps_dev, uint64_t seed, uint64_t offset, const uint64_t* draw_dev, float eps_std,
-                       float min_scale, float max_scale, int batch, int wf, float* out_dev, float* eps_out_dev,
-                       float* noise_out_dev, sept_stream_t stream);
+                       const float* eps_dev, uint64_t seed, uint64_t offset, const uint64_t* draw_dev, int per_sample,
+                       float eps_std, float min_scale, float max_scale, int batch, int wf, float* out_dev,
+                       float* eps_out_dev, float* noise_out_dev, sept_stream_t stream);
 
 /* *counter_dev += inc on the stream (one thread); keeps the draw counter of sept_cloak_fwd_f32 on the device. */
 int sept_counter_add_u64(uint64_t* counter_dev, uint64_t inc, sept_stream_t stream);

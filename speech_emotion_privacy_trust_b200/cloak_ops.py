@@ -37,10 +37,12 @@ def _alias(t: torch.Tensor) -> torch.Tensor:
     return torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage(), t.storage_offset(), t.size(), t.stride())
 
 
-def cloak_forward_raw(x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, want_noise=False, draw=None):
+def cloak_forward_raw(x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, want_noise=False, draw=None,
+                      per_sample=False):
     """One launch of sept_cloak_fwd_f32.  Returns (out, eps_used, noise | None).  x may be None (noise only).
-    draw: optional device int64 counter of draws so far; it selects the Philox offset on the device and is advanced by
-    one after the launch (CUDA-graph friendly: every replay draws a fresh eps)."""
+    draw: optional device int64 counter of draws so far; it selects the Philox offset on the device and is advanced
+    after the launch (CUDA-graph friendly: every replay draws a fresh eps).  per_sample: every batch element gets its own
+    eps (eps, when supplied, is (B, wf)); inference only."""
     _lib.require_cuda(locs)
     wf = locs.numel()
     dev = locs.device
@@ -48,17 +50,17 @@ def cloak_forward_raw(x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale
     if x is not None and x.numel() != batch * wf:
         raise ValueError(f"input of shape {tuple(x.shape)} does not broadcast against locs of shape {tuple(locs.shape)}")
     out = torch.empty_like(x) if x is not None else None
-    eps_used = torch.empty(wf, dtype=torch.float32, device=dev) if eps is None else eps
+    eps_used = torch.empty(batch * wf if per_sample else wf, dtype=torch.float32, device=dev) if eps is None else eps
     noise = torch.empty_like(locs) if want_noise else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().sept_cloak_fwd_f32(
             _ptr(x) if x is not None else locs.data_ptr(), locs.data_ptr(), rhos.data_ptr(), _ptr(mask), _ptr(eps),
-            int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset) & 0xFFFFFFFFFFFFFFFF, _ptr(draw) if eps is None else 0, float(eps_std),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset) & 0xFFFFFFFFFFFFFFFF, _ptr(draw) if eps is None else 0, int(per_sample), float(eps_std),
             float(min_scale), float(max_scale),
             batch, wf, _ptr(out) if out is not None else locs.data_ptr(), eps_used.data_ptr() if eps is None else 0,
             _ptr(noise), _stream(dev)))
         if draw is not None and eps is None:
-            _lib.check(_lib.lib().sept_counter_add_u64(draw.data_ptr(), 1, _stream(dev)))
+            _lib.check(_lib.lib().sept_counter_add_u64(draw.data_ptr(), batch if per_sample else 1, _stream(dev)))
     return out, eps_used, noise
 
 

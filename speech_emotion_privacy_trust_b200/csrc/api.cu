@@ -260,15 +260,16 @@ int sept_normalize_windows_f32(const float* feat, const int64_t* frame_off, cons
 }
 
 int sept_cloak_fwd_f32(const float* x, const float* locs, const float* rhos, const float* mask, const float* eps,
-                       uint64_t seed, uint64_t offset, const uint64_t* draw_dev, float eps_std, float min_scale, float max_scale,
-                       int batch, int wf, float* out, float* eps_out, float* noise_out, sept_stream_t stream) {
+                       uint64_t seed, uint64_t offset, const uint64_t* draw_dev, int per_sample, float eps_std, float min_scale,
+                       float max_scale, int batch, int wf, float* out, float* eps_out, float* noise_out, sept_stream_t stream) {
     if (!x || !locs || !rhos || !out || batch < 0 || wf <= 0) return fail(SEPT_E_BADARG, "sept_cloak_fwd_f32: bad argument");
     if (wf % 4) return fail(SEPT_E_BADARG, "sept_cloak_fwd_f32: W*F=%d must be a multiple of 4", wf);
     if (!aligned16(x) || !aligned16(locs) || !aligned16(rhos) || !aligned16(mask) || !aligned16(eps) || !aligned16(out) ||
         !aligned16(eps_out) || !aligned16(noise_out))
         return fail(SEPT_E_BADARG, "sept_cloak_fwd_f32: pointers must be 16-byte aligned");
     sept::CloakFwdParams p{};
-    p.x = x; p.locs = locs; p.rhos = rhos; p.mask = mask; p.eps = eps; p.seed = seed; p.offset = offset; p.draw_dev = draw_dev;
+    p.x = x; p.locs = locs; p.rhos = rhos; p.mask = mask; p.eps = eps; p.seed = seed; p.offset = offset; p.draw_dev = draw_dev; p.per_sample = per_sample ? 1 : 0;
+    if (per_sample && noise_out) return fail(SEPT_E_BADARG, "sept_cloak_fwd_f32: noise_out is a single (wf) sample; not available with per_sample");
     p.eps_std = eps_std; p.min_scale = min_scale; p.max_scale = max_scale; p.batch = batch; p.wf = wf; p.out = out;
     p.eps_out = eps_out; p.noise_out = noise_out;
     SEPT_CUDA(sept::launch_cloak_fwd(p, static_cast<cudaStream_t>(stream)));

@@ -54,28 +54,39 @@ __device__ __forceinline__ float sigma_of(float rho, float mn, float mx) {
 
 constexpr int kCloakThreads = 128;
 
-__global__ void __launch_bounds__(kCloakThreads) cloak_fwd_kernel(const CloakFwdParams p) {
-    const int i4 = blockIdx.x * kCloakThreads + threadIdx.x;
-    if (i4 * 4 >= p.wf) return;
-    const int i = i4 * 4;
-    const float4 mu = ld4(p.locs + i), rho = ld4(p.rhos + i);
-    const uint64_t off = p.draw_dev ? p.offset + *p.draw_dev * (uint64_t)((p.wf + 3) / 4) : p.offset;
-    float4 e = p.eps ? ld4(p.eps + i) : normal4(p.seed, off, (uint32_t)i4, p.eps_std);
-    if (p.eps_out && blockIdx.y == 0) st4(p.eps_out + i, e);
-    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (p.mask) {
-        m = ld4(p.mask + i);
-        e.x *= m.x; e.y *= m.y; e.z *= m.z; e.w *= m.w;
-    }
+__device__ __forceinline__ float4 cloak_noise4(const CloakFwdParams& p, float4 mu, float4 rho, float4 e, float4 m) {
+    if (p.mask) { e.x *= m.x; e.y *= m.y; e.z *= m.z; e.w *= m.w; }
     float4 nz;
     // product and sum rounded separately, like the reference's two ATen ops (no FMA contraction)
     nz.x = __fadd_rn(mu.x, __fmul_rn(sigma_of(rho.x, p.min_scale, p.max_scale), e.x));
     nz.y = __fadd_rn(mu.y, __fmul_rn(sigma_of(rho.y, p.min_scale, p.max_scale), e.y));
     nz.z = __fadd_rn(mu.z, __fmul_rn(sigma_of(rho.z, p.min_scale, p.max_scale), e.z));
     nz.w = __fadd_rn(mu.w, __fmul_rn(sigma_of(rho.w, p.min_scale, p.max_scale), e.w));
-    if (p.noise_out && blockIdx.y == 0) st4(p.noise_out + i, nz);
+    return nz;
+}
+
+__global__ void __launch_bounds__(kCloakThreads) cloak_fwd_kernel(const CloakFwdParams p) {
+    const int i4 = blockIdx.x * kCloakThreads + threadIdx.x;
+    if (i4 * 4 >= p.wf) return;
+    const int i = i4 * 4;
+    const uint64_t quads = (uint64_t)((p.wf + 3) / 4);
+    const uint64_t off = p.draw_dev ? p.offset + *p.draw_dev * quads : p.offset;
+    const float4 mu = ld4(p.locs + i), rho = ld4(p.rhos + i);
+    const float4 m = p.mask ? ld4(p.mask + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!p.per_sample) {
+        const float4 e = p.eps ? ld4(p.eps + i) : normal4(p.seed, off, (uint32_t)i4, p.eps_std);
+        if (p.eps_out && blockIdx.y == 0) st4(p.eps_out + i, e);
+        nz = cloak_noise4(p, mu, rho, e, m);
+        if (p.noise_out && blockIdx.y == 0) st4(p.noise_out + i, nz);
+    }
     for (int b = blockIdx.y; b < p.batch; b += gridDim.y) {
         const size_t o = (size_t)b * p.wf + i;
+        if (p.per_sample) {
+            const float4 e = p.eps ? ld4(p.eps + o) : normal4(p.seed, off + (uint64_t)b * quads, (uint32_t)i4, p.eps_std);
+            if (p.eps_out) st4(p.eps_out + o, e);
+            nz = cloak_noise4(p, mu, rho, e, m);
+        }
         float4 v = ld4(p.x + o);
         if (p.mask) { v.x = __fmul_rn(v.x, m.x); v.y = __fmul_rn(v.y, m.y); v.z = __fmul_rn(v.z, m.z); v.w = __fmul_rn(v.w, m.w); }
         v.x = __fadd_rn(v.x, nz.x); v.y = __fadd_rn(v.y, nz.y); v.z = __fadd_rn(v.z, nz.z); v.w = __fadd_rn(v.w, nz.w);

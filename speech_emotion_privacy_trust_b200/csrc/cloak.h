@@ -16,6 +16,9 @@ struct CloakFwdParams {
     const float* eps;        // (wf) or null -> Philox(seed, offset)
     uint64_t seed, offset;
     const uint64_t* draw_dev; // null, or device counter: the Philox offset becomes offset + *draw_dev * ceil(wf / 4)
+    int per_sample;          // 0: one (wf) eps for the whole batch (the reference's forward); 1: batch element b has its own
+                             // eps -- eps / eps_out are (B, wf), Philox draw index = *draw_dev + b (a batched stand-in for
+                             // the reference's one-forward-per-window evaluation loop, adversary_cloak_evaluation.py:73-83)
     float eps_std;           // 0.1 in the reference (cloak_models.py:37)
     float min_scale, max_scale;
     int batch, wf;

@@ -214,3 +214,64 @@ def test_distributed_speaker_stats_single_rank_equals_local():
     assert float(db["absent"]["count"][0]) == 0.0
     za, zb = nz.normalize(feat, lay, a), nz.normalize(feat, lay, b)
     assert float((za - zb).abs().max()) < 1e-4
+
+
+def test_batched_evaluation_equals_reference_window_loop(mods):
+    """evaluation.cloak_evaluate (all windows in one forward, per-window eps) against the reference's literal loop
+    (adversary_cloak_evaluation.py:60-93): one window at a time through the cloak layer with the same eps."""
+    cloak_models, _, baseline_models = mods
+    from speech_emotion_privacy_trust_b200 import evaluation, normalization as nz
+    from speech_emotion_privacy_trust_b200.extraction import Layout
+    torch.manual_seed(21)
+    rng = np.random.default_rng(21)
+    frames = [431, 150, 260, 777]
+    spk = ["a", "b", "a", "b"]
+    feats = [(rng.standard_normal((T, 128)) * 6 - 35).astype(np.float32) for T in frames]
+    fo = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+    lay = Layout(fo, torch.from_numpy(fo).cuda(), torch.zeros(len(fo), dtype=torch.int32, device="cuda"))
+    feat = torch.from_numpy(np.concatenate(feats)).cuda()
+    st = nz.speaker_stats(feat, lay, spk, whole_utterance=[True] * 4)
+    mk = lambda pred: baseline_models.two_d_cnn_lstm(1, 128, 5, lstm_hidden_size=64, pred=pred, global_feature=0).cuda().eval()
+    base, adv = mk("emotion"), mk("gender")
+    layer = cloak_models.cloak_noise(0.05 * torch.randn(1, 200, 128), torch.ones(1, 200, 128), 0.01, 5.0, "cuda").cuda()
+    with torch.no_grad():
+        layer.rhos.add_(torch.randn(1, 200, 128, device="cuda"))
+    mask = evaluation.suppression_mask(layer, 40)
+    sig = layer.scales().detach()
+    assert abs(float((mask == 0).float().mean()) - 0.6) < 0.01            # the 60 % largest sigmas are suppressed
+    wu, wt = evaluation.eval_window_table(lay)
+    assert [int((wu == u).sum()) for u in range(4)] == [(431 - 200) // 50 + 1, 1, 2, (777 - 200) // 50 + 1]
+    eps = 0.1 * torch.randn(len(wu), 200, 128, device="cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False    # batch 17 vs batch 1 pick different kernels
+    e_pred, g_pred, e_prob, g_prob = evaluation.cloak_evaluate(layer, base, adv, feat, lay, st, mask=mask, external_eps=eps)
+    from speech_emotion_privacy_trust_b200 import cloak_ops
+    xw = nz.normalized_windows(feat, lay, st, wu, wt)
+    noisy_all, _, _ = cloak_ops.cloak_forward_raw(xw, layer.locs.detach().contiguous(), layer.rhos.detach().contiguous(), mask.contiguous(),
+                                                  eps.reshape(-1), 0, 0, 0.1, 0.01, 5.0, per_sample=True)
+    # the reference loop
+    z = nz.normalize(feat, lay, st)
+    zero_row = nz.normalized_windows(feat, lay, st, np.array([1], np.int32), np.array([0], np.int32))[0, 0, -1]   # padded row of utt 1
+    w = 0
+    for u, T in enumerate(frames):
+        pe, pg = [], []
+        for i in range(max(1, (T - 200) // 50 + 1)):
+            win = z[fo[u] + i * 50: min(fo[u + 1], fo[u] + i * 50 + 200)]
+            if win.shape[0] < 200:
+                win = torch.cat([win, zero_row.expand(200 - win.shape[0], 128)], 0)
+            layer.external_eps = eps[w:w + 1]
+            with torch.no_grad():
+                noisy = layer(win[None, None].contiguous(), mask)
+                assert torch.equal(noisy[0], noisy_all[w])              # the per-window eps path is bit identical
+                pe.append(torch.softmax(base(noisy), 1)[0])
+                pg.append(torch.softmax(adv(noisy), 1)[0])
+            w += 1
+        me, mg = torch.stack(pe).mean(0).cpu().numpy(), torch.stack(pg).mean(0).cpu().numpy()
+        assert np.max(np.abs(me - e_prob[u])) < 2e-4 and np.max(np.abs(mg - g_prob[u])) < 2e-4
+        assert int(np.argmax(me)) == int(e_pred[u]) and int(np.argmax(mg)) == int(g_pred[u])
+    layer.external_eps = None
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    # device-drawn noise: per-window samples differ, and the draw counter advanced by the number of windows
+    before = int(layer._eps_source()[2].item()) if layer._draws is not None else 0
+    evaluation.cloak_evaluate(layer, base, adv, feat, lay, st, mask=None)
+    assert int(layer._draws.item()) - before == len(wu)
