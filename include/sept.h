@@ -78,6 +78,18 @@ int sept_mfcc_f32(const float* wav_dev, const int64_t* utt_off_dev, const int64_
                   const int32_t* item_off_dev, int n_utts, int64_t total_frames, float* scratch_dev,
                   int32_t* utt_max_dev, float* out_dev, sept_stream_t stream);
 
+/* ---- resampling ahead of extraction --------------------------------------------------------------------------------
+ * Band-limited sinc resampling of a ragged batch.  Replaces torchaudio.transforms.Resample(sample_rate, 16000) as the
+ * reference applies it to the 44.1 kHz MSP-Improv corpus (feature_extraction/audio_feature_extraction.py:139-141 ->
+ * torchaudio/functional/functional.py _get_sinc_resample_kernel/_apply_sinc_resample_kernel: sinc_interp_hann,
+ * lowpass_filter_width 6, rolloff 0.99).  Output length per utterance: ceil(new_freq * n / orig_freq). */
+
+/* HOST helper: out_off_host[n_utts+1] from in_off_host[n_utts+1]. */
+int sept_resample_layout(const int64_t* in_off_host, int n_utts, int orig_freq, int new_freq, int64_t* out_off_host);
+
+int sept_resample_f32(const float* in_dev, const int64_t* in_off_dev, const int64_t* out_off_dev, int n_utts,
+                      int64_t total_out, int orig_freq, int new_freq, float* out_dev, sept_stream_t stream);
+
 /* ---- per-speaker normalisation (preprocess_data/preprocess_adversary_data.py:26-27, 41-48, 357-385) -------------
  * feat_dev: (total_frames, n_feat) frame-major features; a frame that lies in k training windows (win_len, shift_len)
  * counts k times, utterances flagged in whole_dev (test split) count every frame once.

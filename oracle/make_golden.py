@@ -172,6 +172,23 @@ def norm_fixture():
     print("norm.npz: windows", n_out, "speakers", list(ns["training_norm_dict"]))
 
 
+def resample_fixture():
+    """torchaudio.transforms.Resample(44100, 16000), the call of audio_feature_extraction.py:140-141, on synthetic
+    44.1 kHz audio (third-party dependency of the reference; version 2.11.0 in this container)."""
+    import torchaudio
+    rng = np.random.default_rng(4410)
+    out = {}
+    for i, n in enumerate((441, 4410, 10007, 30000)):
+        w = synth.speech_shaped(n, rng)
+        out[f"in{i}"] = w
+        out[f"out{i}"] = torchaudio.transforms.Resample(44100, 16000)(torch.from_numpy(w)[None])[0].numpy()
+    w = synth.speech_shaped(9000, rng)
+    out["in_48k"] = w
+    out["out_48k"] = torchaudio.transforms.Resample(48000, 16000)(torch.from_numpy(w)[None])[0].numpy()
+    np.savez_compressed(OUT / "resample.npz", **out)
+    print("resample.npz:", {k: v.shape for k, v in out.items() if k.startswith("out")})
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     afe, cloak_models, reversal_gradient, baseline_models = import_reference()
@@ -180,3 +197,4 @@ if __name__ == "__main__":
     cloak_fixture(cloak_models, reversal_gradient)
     model_keys_fixture(cloak_models, baseline_models)
     norm_fixture()
+    resample_fixture()

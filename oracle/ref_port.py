@@ -45,3 +45,8 @@ def extract_all(audio: torch.Tensor) -> dict:
     """What one iteration of the reference's per-file loop computes (reference :185-187)."""
     return {"mfcc": mfcc(audio), "mel1": mel_spectrogram(audio, n_fft=800, feature_len=128),
             "mel2": mel_spectrogram(audio, n_fft=1600, feature_len=128)}
+
+
+def resample(audio: torch.Tensor, sample_rate: int, new_rate: int = SAMPLE_RATE) -> torch.Tensor:
+    """What the reference does to a 44.1 kHz file before extraction (reference :139-141)."""
+    return torchaudio.transforms.Resample(sample_rate, new_rate)(audio)

@@ -14,6 +14,7 @@
 #include "cloak.h"
 #include "extract.h"
 #include "norm.h"
+#include "resample.h"
 #include "tables.h"
 
 namespace {
@@ -50,6 +51,14 @@ struct ExtractConsts {
     void* mel_bands = nullptr;
     int n_wquads = 0;
 };
+
+struct ResampleConsts {
+    int32_t* k_lo = nullptr;
+    float* w = nullptr;
+    int taps = 0, width = 0;
+};
+
+std::map<std::tuple<int, int, int>, ResampleConsts> g_resample;
 
 std::mutex g_mu;
 std::map<std::tuple<int, int, int>, ExtractConsts> g_consts;
@@ -105,6 +114,27 @@ int get_dct(float** out) {
         float* dd = nullptr;
         SEPT_CUDA(upload(d, &dd));
         it = g_dct.emplace(dev, dd).first;
+    }
+    *out = it->second;
+    return SEPT_OK;
+}
+
+long long gcd_ll(long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; }
+
+int get_resample(int orig, int up, ResampleConsts* out) {
+    int dev = 0;
+    SEPT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(dev, orig, up);
+    auto it = g_resample.find(key);
+    if (it == g_resample.end()) {
+        ResampleConsts c;
+        std::vector<int32_t> k_lo;
+        std::vector<float> rows;
+        c.width = sept::make_resample_rows(orig, up, k_lo, rows, c.taps);
+        SEPT_CUDA(upload(k_lo, &c.k_lo));
+        SEPT_CUDA(upload(rows, &c.w));
+        it = g_resample.emplace(key, c).first;
     }
     *out = it->second;
     return SEPT_OK;
@@ -217,6 +247,38 @@ int sept_mfcc_f32(const float* wav, const int64_t* utt_off, const int64_t* frame
     d.power = scratch; d.utt_max = utt_max; d.frame_utt = p.frame_utt; d.frame_off = frame_off; d.dct = dct; d.n_utts = n_utts;
     d.total_frames = total_frames; d.top_db = 80.0f; d.out = out;
     SEPT_CUDA(sept::launch_mfcc_dct(d, st));
+    return SEPT_OK;
+}
+
+int sept_resample_layout(const int64_t* in_off, int n_utts, int orig_freq, int new_freq, int64_t* out_off) {
+    if (!in_off || !out_off || n_utts < 0 || orig_freq <= 0 || new_freq <= 0)
+        return fail(SEPT_E_BADARG, "sept_resample_layout: bad argument");
+    const long long g = gcd_ll(orig_freq, new_freq), orig = orig_freq / g, up = new_freq / g;
+    out_off[0] = 0;
+    for (int u = 0; u < n_utts; ++u) {
+        const long long n = in_off[u + 1] - in_off[u];
+        if (n < 0) return fail(SEPT_E_BADARG, "sept_resample_layout: offsets must be non-decreasing");
+        out_off[u + 1] = out_off[u] + (up * n + orig - 1) / orig;     // ceil(new * length / orig), functional.py
+    }
+    return SEPT_OK;
+}
+
+int sept_resample_f32(const float* in, const int64_t* in_off, const int64_t* out_off, int n_utts, int64_t total_out,
+                      int orig_freq, int new_freq, float* out, sept_stream_t stream) {
+    if (n_utts == 0 || total_out == 0) return SEPT_OK;
+    if (!in || !in_off || !out_off || !out || n_utts < 0 || total_out < 0 || orig_freq <= 0 || new_freq <= 0)
+        return fail(SEPT_E_BADARG, "sept_resample_f32: bad argument");
+    const long long g = gcd_ll(orig_freq, new_freq), orig = orig_freq / g, up = new_freq / g;
+    if (orig > 4096 || up > 4096)
+        return fail(SEPT_E_UNSUPPORTED, "sept_resample_f32: %d -> %d reduces to %lld/%lld, beyond the 4096-phase table limit",
+                    orig_freq, new_freq, up, orig);
+    ResampleConsts c;
+    int rc = get_resample((int)orig, (int)up, &c);
+    if (rc) return rc;
+    sept::ResampleParams p{};
+    p.in = in; p.in_off = in_off; p.out_off = out_off; p.n_utts = n_utts; p.orig = (int)orig; p.up = (int)up;
+    p.width = c.width; p.taps = c.taps; p.k_lo = c.k_lo; p.w = c.w; p.out = out; p.total_out = total_out;
+    SEPT_CUDA(sept::launch_resample(p, static_cast<cudaStream_t>(stream)));
     return SEPT_OK;
 }
 

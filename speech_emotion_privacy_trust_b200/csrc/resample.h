@@ -1,0 +1,24 @@
+// Launch parameters of the polyphase sinc resampler (resample.cu).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sept {
+
+struct ResampleParams {
+    const float* in;            // ragged input, all utterances back to back
+    const int64_t* in_off;      // [n_utts + 1]
+    const int64_t* out_off;     // [n_utts + 1], length ceil(new * n_in / orig) per utterance
+    int n_utts;
+    int orig, up;               // orig_freq / gcd, new_freq / gcd
+    int width;                  // zero-crossing half width in input samples (torchaudio's `width`)
+    int taps;                   // stored taps per phase
+    const int32_t* k_lo;        // [up] first stored tap of each phase (index into the torchaudio kernel row)
+    const float* w;             // [up][taps] kernel rows restricted to their non-zero support
+    float* out;
+    long long total_out;
+};
+
+cudaError_t launch_resample(const ResampleParams& p, cudaStream_t stream);
+
+}  // namespace sept

@@ -112,4 +112,41 @@ inline std::vector<float> make_dct_ortho(int n_mfcc, int n_mels) {
     return d;
 }
 
+// Polyphase rows of torchaudio's sinc_interp_hann resampling kernel (functional.py: _get_sinc_resample_kernel,
+// lowpass_filter_width 6, rolloff 0.99), evaluated in double like torchaudio (dtype None) and rounded to float, each row
+// cut to a common-length window [k_lo[j], k_lo[j] + taps) that covers its non-zero support.  orig/up are the
+// gcd-reduced rates.  Returns torchaudio's `width`.
+inline int make_resample_rows(int orig, int up, std::vector<int32_t>& k_lo, std::vector<float>& rows, int& taps) {
+    const int lpw = 6;
+    const double rolloff = 0.99;
+    const double base_freq = (double)(orig < up ? orig : up) * rolloff;
+    const int width = (int)std::ceil((double)lpw * orig / base_freq);
+    const int K = 2 * width + orig;
+    std::vector<double> full((size_t)up * K);
+    std::vector<int> first(up, K), last(up, -1);
+    for (int j = 0; j < up; ++j)
+        for (int k = 0; k < K; ++k) {
+            double t = ((double)(-j) / up + (double)(k - width) / orig) * base_freq;
+            const bool inside = t > -lpw && t < lpw;
+            if (t < -lpw) t = -lpw;
+            if (t > lpw) t = lpw;
+            const double window = std::pow(std::cos(t * M_PI / lpw / 2.0), 2.0);
+            const double tp = t * M_PI;
+            const double v = (tp == 0.0 ? 1.0 : std::sin(tp) / tp) * window * (base_freq / orig);
+            full[(size_t)j * K + k] = v;
+            if (inside) { if (k < first[j]) first[j] = k; if (k > last[j]) last[j] = k; }
+        }
+    taps = 0;
+    for (int j = 0; j < up; ++j) if (last[j] - first[j] + 1 > taps) taps = last[j] - first[j] + 1;
+    k_lo.assign(up, 0);
+    rows.assign((size_t)up * taps, 0.f);
+    for (int j = 0; j < up; ++j) {
+        int lo = first[j];
+        if (lo + taps > K) lo = K - taps;
+        k_lo[j] = lo;
+        for (int k = 0; k < taps; ++k) rows[(size_t)j * taps + k] = (float)full[(size_t)j * K + lo + k];
+    }
+    return width;
+}
+
 }  // namespace sept

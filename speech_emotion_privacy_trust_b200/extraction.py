@@ -72,6 +72,26 @@ class RaggedAudio:
         return self._layouts[key]
 
 
+def resample(batch: "RaggedAudio", orig_freq: int, new_freq: int = SAMPLE_RATE) -> "RaggedAudio":
+    """Band-limited sinc resampling of every utterance (torchaudio.transforms.Resample(orig_freq, new_freq) as the
+    reference applies it to 44.1 kHz corpora, audio_feature_extraction.py:139-141); returns a new ragged batch."""
+    if orig_freq == new_freq:
+        return batch
+    n = batch.n_utts
+    out_off = np.zeros(n + 1, dtype=np.int64)
+    _lib.check(_lib.lib().sept_resample_layout(batch.utt_off_host.ctypes.data, n, orig_freq, new_freq, out_off.ctypes.data))
+    dev = batch.wav.device
+    out = torch.empty(int(out_off[-1]), dtype=torch.float32, device=dev)
+    d_out_off = torch.from_numpy(out_off).to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sept_resample_f32(batch.wav.data_ptr(), batch.utt_off.data_ptr(), d_out_off.data_ptr(), n,
+                                                int(out_off[-1]), orig_freq, new_freq, out.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream))
+    res = RaggedAudio.__new__(RaggedAudio)
+    res.wav, res.utt_off_host, res.utt_off, res._layouts = out, out_off, d_out_off, {}
+    return res
+
+
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 

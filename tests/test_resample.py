@@ -1,0 +1,74 @@
+"""Sinc resampler (the step before the hot path for 44.1 kHz corpora): oracle vs the golden vectors produced by
+torchaudio.transforms.Resample -- the call the reference makes (audio_feature_extraction.py:139-141) --, the library's
+row table vs the oracle kernel (CPU), and the CUDA kernel vs both (GPU)."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+
+REPO = Path(__file__).resolve().parents[1]
+GOLD = np.load(REPO / "tests" / "golden" / "resample.npz")
+TOL = 5e-6          # absolute, signals peak-normalised to 0.3: fp32 accumulation over ~35 (here) or 475 (torchaudio) taps
+
+
+def test_oracle_matches_torchaudio_golden():
+    for i in range(4):
+        y = restate.resample(GOLD[f"in{i}"], 44100, 16000)
+        assert y.shape == GOLD[f"out{i}"].shape                      # ceil(16000 * n / 44100)
+        assert np.max(np.abs(y - GOLD[f"out{i}"])) < TOL
+    assert np.max(np.abs(restate.resample(GOLD["in_48k"], 48000, 16000) - GOLD["out_48k"])) < TOL
+    assert [len(restate.resample(np.zeros(n), 44100, 16000)) for n in (1, 441, 442, 44100)] == [1, 160, 161, 16000]
+
+
+@pytest.mark.parametrize("orig,up,rates", [(441, 160, (44100, 16000)), (3, 1, (48000, 16000)), (1, 2, (8000, 16000))])
+def test_library_row_table_matches_oracle_kernel(tmp_path, orig, up, rates):
+    exe = tmp_path / "rows"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", str(REPO / "speech_emotion_privacy_trust_b200" / "csrc"),
+                    str(REPO / "tests" / "hostsim" / "resample_rows.cpp"), "-o", str(exe)], check=True)
+    subprocess.run([str(exe), str(orig), str(up), str(tmp_path / "rows.bin")], check=True)
+    raw = np.fromfile(tmp_path / "rows.bin", np.int32)
+    width, taps = int(raw[0]), int(raw[1])
+    k_lo = raw[2:2 + up]
+    rows = raw[2 + up:].view(np.float32).reshape(up, taps)
+    kern, w_ref, o_ref, n_ref = restate.sinc_resample_kernel(*rates)
+    assert (width, orig, up) == (w_ref, o_ref, n_ref)
+    full = np.zeros_like(kern)
+    kept = np.zeros(kern.shape, dtype=bool)
+    for j in range(up):
+        full[j, k_lo[j]:k_lo[j] + taps] = rows[j]
+        kept[j, k_lo[j]:k_lo[j] + taps] = True
+    assert np.max(np.abs(full - kern)[kept]) < 1e-7                   # float rounding of the kept taps
+    assert np.max(np.abs(kern[~kept]), initial=0.0) < 1e-30           # what is cut off: cos^2(pi/2) residue of the window
+    assert taps <= 2 * width + 4
+
+
+@pytest.mark.gpu
+def test_cuda_resampler_vs_golden_and_oracle():
+    from speech_emotion_privacy_trust_b200 import extraction, synth
+    waves = [GOLD[f"in{i}"] for i in range(4)]
+    batch = extraction.RaggedAudio.from_list(waves)
+    out = extraction.resample(batch, 44100, 16000)
+    off = out.utt_off_host
+    for i in range(4):
+        got = out.wav[off[i]:off[i + 1]].cpu().numpy()
+        assert got.shape == GOLD[f"out{i}"].shape
+        assert np.max(np.abs(got - GOLD[f"out{i}"])) < TOL
+        assert np.max(np.abs(got - restate.resample(waves[i], 44100, 16000))) < TOL
+    b48 = extraction.RaggedAudio.from_list([GOLD["in_48k"]])
+    assert np.max(np.abs(extraction.resample(b48, 48000, 16000).wav.cpu().numpy() - GOLD["out_48k"])) < TOL
+    # MSP-Improv-shaped path: 44.1 kHz -> 16 kHz -> log-mel equals log-mel of the oracle's resampled audio
+    rng = np.random.default_rng(12)
+    w44 = [synth.speech_shaped(int(n), rng) for n in (44100, 61234, 30011)]
+    r = extraction.resample(extraction.RaggedAudio.from_list(w44), 44100)
+    mel, lay = extraction.logmel(r, n_fft=800)
+    fo = lay.frame_off_host
+    for u, w in enumerate(w44):
+        ref = restate.mel_spectrogram(restate.resample(w, 44100, 16000)[None], 800, 128, dtype=np.float64)[0]
+        got = mel[fo[u]:fo[u + 1]].cpu().numpy().T
+        strong = ref > ref.max(axis=0, keepdims=True) - 50.0
+        assert got.shape == ref.shape and np.max(np.abs(got - ref)[strong]) < 1e-3
+    assert extraction.resample(r, 16000, 16000) is r
