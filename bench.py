@@ -339,10 +339,11 @@ def cpu_baseline():
 def secondary_metrics(args, dev, rank, world, batch=None, hours=None):
     """BASELINE.json's second figure: cloak+GRL training utterances/sec (config 3), data parallel, B=32 per GPU; plus the
     other features the reference's extraction script computes per utterance (this rank's numbers, device resident)."""
-    from benchmarks_train import eval_throughput, train_throughput
+    from benchmarks_train import cloak_kernel_bandwidth, eval_throughput, train_throughput
     out = train_throughput(dev, rank, world, steps=20, warmup=5)
     if rank == 0:
         out["cloak_eval"] = eval_throughput(dev)
+        out["cloak_kernels"] = cloak_kernel_bandwidth(dev)
     if batch is not None:
         out["other_features_this_rank"] = other_features(batch, hours, dev)
     return out

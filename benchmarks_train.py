@@ -134,3 +134,42 @@ def eval_throughput(dev, n_utts=64, steps=5, seed=8):
     ms = e0.elapsed_time(e1) / steps
     return {"metric": "cloak evaluation windows/sec", "value": n_win / (ms * 1e-3), "unit": "windows/s", "utterances_per_s": n_utts / (ms * 1e-3),
             "utterances": n_utts, "windows": n_win, "ms_per_pass": ms, "max_windows_per_forward": 512}
+
+
+def cloak_kernel_bandwidth(dev, batch=64, reps=64):
+    """Achieved HBM GB/s of the fused cloak forward and cloak+GRL backward kernels at B=64, W=200, F=128 (config 2).
+    16 distinct input/output sets (16 x 13 MB > the 126 MB L2) are cycled so that the traffic comes from HBM."""
+    from speech_emotion_privacy_trust_b200 import cloak_ops
+    W, F, sets = 200, 128, 16
+    wf = W * F
+    xs = [torch.randn(batch, 1, W, F, device=dev) for _ in range(sets)]
+    gb = [torch.randn(batch, 1, W, F, device=dev) for _ in range(sets)]
+    locs, rhos = torch.zeros(wf, device=dev), torch.full((wf,), -2.0, device=dev)
+    eps = 0.1 * torch.randn(wf, device=dev)
+    lib = cloak_ops._lib.lib()
+    ws = cloak_ops._workspace(dev, wf)
+    outs = [torch.empty_like(xs[0]) for _ in range(sets)]
+    dlocs, drhos = torch.empty(wf, device=dev), torch.empty(wf, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def fwd(i):
+        cloak_ops._lib.check(lib.sept_cloak_fwd_f32(xs[i].data_ptr(), locs.data_ptr(), rhos.data_ptr(), 0, eps.data_ptr(), 0, 0, 0, 0,
+                                                    0.1, 0.01, 10.0, batch, wf, outs[i].data_ptr(), 0, 0, st))
+
+    def bwd(i):
+        cloak_ops._lib.check(lib.sept_cloak_grl_bwd_f32(xs[i].data_ptr(), gb[i].data_ptr(), 0.1, eps.data_ptr(), rhos.data_ptr(), 0,
+                                                        0.01, 10.0, batch, wf, ws.data_ptr(), dlocs.data_ptr(), drhos.data_ptr(), 0, st))
+    res = {}
+    for name, fn, nbytes in (("cloak_fwd", fwd, 2 * batch * wf * 4 + 3 * wf * 4), ("cloak_grl_bwd", bwd, 2 * batch * wf * 4 + 4 * wf * 4)):
+        for i in range(sets):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(reps):
+            fn(r % sets)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        res[name] = {"us_per_launch": us, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / us * 1e-3}
+    return res
