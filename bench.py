@@ -87,7 +87,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "-i", str(index), "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -117,6 +117,16 @@ class ClockSampler:
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+
+
+def profiled_traffic(frames: int):
+    """DRAM bytes per launch of the extraction kernel from the committed ncu capture (profiles/), scaled per frame when
+    the workload size differs; None if no capture is committed."""
+    p = REPO / "profiles" / "extract800_traffic_r01.json"
+    if N_FFT != 800 or not p.exists():
+        return None
+    t = json.loads(p.read_text())
+    return int((t["dram_bytes_read"] + t["dram_bytes_write"]) * frames / t["frames"])
 
 
 def measured_peaks():
@@ -287,7 +297,7 @@ def run_b200(args):
                     "api": "extraction.logmel_host(pinned host wav, utt_off) -> pinned host (frames,128)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                         "traffic": None, "kernel": "extract_kernel<16, frame-major>", "kernel_ms": k_ms,
+                         "traffic": profiled_traffic(frames), "algorithmic_bytes": BYTES_PER_FRAME * frames, "kernel": "extract_kernel<16, frame-major>", "kernel_ms": k_ms,
                          "algorithmic_flop_per_frame": FLOP_PER_FRAME, "frames_per_launch": frames,
                          "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json ({peak_src}); "
                                         "the path is FP32-CUDA-core bound, not HBM or tensor bound (SURVEY 8d)",
@@ -391,7 +401,7 @@ def other_features(batch, hours, dev, steps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary metric, e2e and cpu_baseline (profiling runs)")
