@@ -59,6 +59,53 @@ struct ItemRef {
     bool interior;
 };
 
+struct MelJob {
+    long long f0;          // first output frame of the utterance
+    int T, t0, u, stream;  // frames of the utterance, first frame of the item, utterance, MFCC stream
+};
+
+// mel bands [m_begin, m_end) (multiples of 32) of every frame pair of one item: sparse dot products over the power
+// tile, log, store; lane = band.  Every lane runs every round (the trip count is warp uniform).
+template <class G, int MODE>
+__device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const f4* melw, const band_t* bands, int n_mels,
+                                           const ExtractParams& prm, const MelJob& job, int m_begin, int m_end) {
+    float vmax = 0.f;
+    for (int m0 = m_begin; m0 < m_end; m0 += 32) {
+        const int m = m0 + lane < n_mels ? m0 + lane : n_mels - 1;
+        const bool live = m0 + lane < n_mels;
+        pk2 acc[G::PPW];
+        const band_t info = bands[m];
+        mel_band<G>(P, melw, info, __shfl_sync(0xffffffffu, info.nq, 0), acc);
+#pragma unroll
+        for (int p = 0; p < G::PPW; ++p) {
+            const int ta = live ? job.t0 + 2 * p : job.T;         // lanes past the last band store nothing
+            const float va = lo(acc[p]), vb = hi(acc[p]);
+            if (MODE == kModeDbFrameMajor) {
+                float* o = prm.out + (job.f0 + ta) * n_mels + m;
+                if (ta < job.T) o[0] = power_to_db(va);
+                if (ta + 1 < job.T) o[n_mels] = power_to_db(vb);
+            } else if (MODE == kModeDbBandMajor) {
+                float* o = prm.out + job.f0 * n_mels + (long long)m * job.T + ta;
+                if (ta < job.T) o[0] = power_to_db(va);
+                if (ta + 1 < job.T) o[1] = power_to_db(vb);
+            } else {                                              // raw mel power, frame major, per stream
+                float* o = prm.out + ((long long)job.stream * prm.total_frames + job.f0 + ta) * n_mels + m;
+                if (ta < job.T) { o[0] = va; vmax = fmaxf(vmax, va); }
+                if (ta + 1 < job.T) { o[n_mels] = vb; vmax = fmaxf(vmax, vb); }
+            }
+        }
+    }
+    if (MODE == kModeMfccPower) {
+        if (m_begin == 0 && job.stream == 0 && lane < G::FPW && job.t0 + lane < job.T)
+            prm.frame_utt[job.f0 + job.t0 + lane] = job.u;        // saves the DCT kernel a search per frame
+        // per-utterance max of the mel power (top_db floor, functional.py:393-402); non-negative floats order like
+        // their bit patterns
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+        if (lane == 0) atomicMax(prm.utt_max + (long long)job.stream * prm.n_utts + job.u, __float_as_int(vmax));
+    }
+}
+
 template <int R, int MODE, int WMAX>
 __global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractParams prm) {
     using G = Geo<R>;
@@ -176,46 +223,16 @@ __global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractPara
             __syncwarp();
 
             // ---- mel bands (lane = band, all frame pairs of the item) + log + store --------------------------
-            float vmax = 0.f;
-            for (int m0 = 0; m0 < n_mels; m0 += 32) {            // uniform over the warp: every lane runs every round
-                const int m = m0 + lane < n_mels ? m0 + lane : n_mels - 1;
-                const bool live = m0 + lane < n_mels;
-                pk2 acc[G::PPW];
-                const band_t info = bands[m];
-                mel_band<G>(P, melw, info, __shfl_sync(0xffffffffu, info.nq, 0), acc);
-#pragma unroll
-                for (int p = 0; p < G::PPW; ++p) {
-                    const int ta = live ? cur.t0 + 2 * p : cur.T;   // lanes past the last band store nothing
-                    const float va = lo(acc[p]), vb = hi(acc[p]);
-                    if (MODE == kModeDbFrameMajor) {
-                        float* o = prm.out + (cur.f0 + ta) * n_mels + m;
-                        if (ta < cur.T) o[0] = power_to_db(va);
-                        if (ta + 1 < cur.T) o[n_mels] = power_to_db(vb);
-                    } else if (MODE == kModeDbBandMajor) {
-                        float* o = prm.out + cur.f0 * n_mels + (long long)m * cur.T + ta;
-                        if (ta < cur.T) o[0] = power_to_db(va);
-                        if (ta + 1 < cur.T) o[1] = power_to_db(vb);
-                    } else {                                      // raw mel power, frame major, per stream
-                        float* o = prm.out + ((long long)stream * prm.total_frames + cur.f0 + ta) * n_mels + m;
-                        if (ta < cur.T) { o[0] = va; vmax = fmaxf(vmax, va); }
-                        if (ta + 1 < cur.T) { o[n_mels] = vb; vmax = fmaxf(vmax, vb); }
-                    }
-                }
-            }
-            if (MODE == kModeMfccPower) {
-                if (stream == 0 && lane < G::FPW && cur.t0 + lane < cur.T)
-                    prm.frame_utt[cur.f0 + cur.t0 + lane] = cur.u;   // saves the DCT kernel a search per frame
-                // per-utterance max of the mel power (top_db floor, functional.py:393-402); non-negative floats
-                // order like their bit patterns
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-                if (lane == 0) atomicMax(prm.utt_max + (long long)stream * prm.n_utts + cur.u, __float_as_int(vmax));
+            {
+                const MelJob job{cur.f0, cur.T, cur.t0, cur.u, stream};
+                mel_rounds<G, MODE>(lane, P, melw, bands, n_mels, prm, job, 0, n_mels);
             }
             __syncwarp();                                        // P reads done before the next pass 1 overwrites Y
             if (stream == n_streams - 1) cur = nxt;
         }
     }
 }
+
 
 // ---- MFCC phase 2: dB with the per-utterance floor, then DCT (transforms/_transforms.py:714-717) ------------
 // One CTA handles kDctFrames consecutive global frames (they may straddle utterances).  The load phase converts the

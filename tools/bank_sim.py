@@ -167,3 +167,39 @@ def search2(R=16):
     out.sort()
     for o in out[:12]:
         print("total %d stores %d mel %d | align %d width %d  pos = k + (k>>%d)*%d" % o)
+
+
+def segments(n_fft, n_mels=128):
+    """bins grouped by the mel segment [f_s, f_{s+1}) they fall in (s = 0 .. n_mels); returns (k_start, n_bins) per
+    segment, derived from the dense filterbank: bin k has rising weight in band s and falling weight in band s-1"""
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+    from oracle import restate
+    import math
+    n_freqs = n_fft // 2 + 1
+    m_max = 2595.0 * math.log10(1.0 + 8000.0 / 700.0)
+    m_pts = np.linspace(0.0, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    freqs = np.linspace(0, 8000, n_freqs)
+    seg = np.searchsorted(f_pts, freqs, side="right") - 1          # f_pts[seg] <= f < f_pts[seg+1]
+    seg = np.clip(seg, 0, n_mels)
+    out = []
+    for s in range(n_mels + 1):
+        ks = np.nonzero(seg == s)[0]
+        out.append((int(ks[0]), len(ks)) if len(ks) else (0, 0))
+    return out
+
+
+def mel_segment_wf(R, pos, PP, segs, lanes_per_round=26):
+    PPW = 32 // R
+    tot_wf = tot_steps = 0
+    for r0 in range(0, len(segs), lanes_per_round):
+        grp = segs[r0:r0 + lanes_per_round]
+        steps = max(n for _, n in grp)
+        tot_steps += steps
+        for t in range(steps):
+            aw = [8 * (k0 + t) if (l < len(grp) and t < grp[l][1]) else None for l, (k0, _) in enumerate(grp + [(0, 0)] * (32 - len(grp)))]
+            tot_wf += wavefronts(aw, 8)                                  # (u, d) weight pair of the bin
+            for p in range(PPW):
+                a = [8 * (p * PP + pos(k0 + t)) if t < n else None for (k0, n) in grp] + [None] * (32 - len(grp))
+                tot_wf += wavefronts(a, 8)
+    return tot_wf, tot_steps
