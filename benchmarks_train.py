@@ -173,3 +173,26 @@ def cloak_kernel_bandwidth(dev, batch=64, reps=64):
         us = e0.elapsed_time(e1) * 1e3 / reps
         res[name] = {"us_per_launch": us, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / us * 1e-3}
     return res
+
+
+def train_cpu_baseline(batch=32, steps=2, warmup=1):
+    """The reference's training step on the host cores (oracle/train_port.py: CPU eps, float64 batch, per-sample loss
+    loop, SGD), the baseline of the secondary metric; a bounded sample of `steps` batches."""
+    import os
+    import time
+    from oracle import train_port
+    from speech_emotion_privacy_trust_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = train_port.build("cpu").train()
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-3, momentum=0.9, weight_decay=1e-4)
+    x, emo, gen, _ = synth.cloak_windows(batch, seed=8)
+    x64, emo, gen, w = torch.from_numpy(x).double(), torch.from_numpy(emo), torch.from_numpy(gen), torch.ones(batch)
+    for _ in range(warmup):
+        train_port.train_step(model, opt, x64, emo, gen, w, "cpu")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_port.train_step(model, opt, x64, emo, gen, w, "cpu")
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": batch / dt, "unit": "utterances/s", "cores": threads, "kind": "port", "ms_per_step": dt * 1e3,
+            "sample": f"{steps} steps of B={batch} after {warmup} warm-up, reference-style step (oracle/train_port.py)"}
