@@ -79,44 +79,55 @@ def synth_corpus_device(lengths: np.ndarray, seed: int, device, chunk: int = 128
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every ~5 ms through NVML while the timed region runs (the nvidia-smi query of
+    B200_PROFILING.md cannot sample faster than its process start-up; NVML reads the same counters)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.rows, self.proc = [], None
+        self.rows, self.stop_flag, self.thread, self.nvml = [], False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                         text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def window(self, t0, t1):
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            parts = [p.strip() for p in r.split(",")]
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, flag in zip(names, parts[2:6]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        sm = [r[1] for r in rows]
+        reasons = sorted(name for name, bit in self.REASONS.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": getattr(self, "max_mhz", None),
+                "reasons": reasons, "samples": len(sm), "source": "nvml"}
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
+        self.stop_flag = True
 
 
 def profiled_traffic(frames: int):
