@@ -53,8 +53,8 @@ def cloak_evaluate(noise_layer, baseline_model, adversary_model, feat: torch.Ten
     win_utt, win_t0 = eval_window_table(lay, utts)
     n_win, n_utt = len(win_utt), len(utts)
     slot = {u: i for i, u in enumerate(utts)}
-    seg = torch.from_numpy(np.fromiter((slot[int(u)] for u in win_utt), dtype=np.int64, count=n_win)).to(dev)
-    counts = torch.bincount(seg, minlength=n_utt).clamp_min(1).unsqueeze(1).float()
+    seg_host = np.fromiter((slot[int(u)] for u in win_utt), dtype=np.int64, count=n_win)      # non-decreasing
+    counts = torch.from_numpy(np.maximum(np.bincount(seg_host, minlength=n_utt), 1)).to(dev).unsqueeze(1).float()
     locs, rhos = noise_layer.locs.detach().float().contiguous(), noise_layer.rhos.detach().float().contiguous()
     mask_c = None if mask is None else mask.detach().to(dev).float().contiguous()
     emo_sum = gen_sum = None
@@ -74,8 +74,11 @@ def cloak_evaluate(noise_layer, baseline_model, adversary_model, feat: torch.Ten
         if emo_sum is None:
             emo_sum = torch.zeros((n_utt, p_emo.shape[1]), device=dev)
             gen_sum = torch.zeros((n_utt, p_gen.shape[1]), device=dev)
-        emo_sum.index_add_(0, seg[a:b], p_emo)
-        gen_sum.index_add_(0, seg[a:b], p_gen)
+        # windows of an utterance are contiguous: a segmented sum (no atomics) keeps the result deterministic
+        first, last = int(seg_host[a]), int(seg_host[b - 1])
+        lengths = torch.from_numpy(np.bincount(seg_host[a:b] - first, minlength=last - first + 1)).to(dev)
+        emo_sum[first:last + 1] += torch.segment_reduce(p_emo.float(), "sum", lengths=lengths, axis=0)
+        gen_sum[first:last + 1] += torch.segment_reduce(p_gen.float(), "sum", lengths=lengths, axis=0)
     emo_prob, gen_prob = emo_sum / counts, gen_sum / counts
     out = torch.cat([emo_prob.argmax(1, keepdim=True).float(), gen_prob.argmax(1, keepdim=True).float(), emo_prob, gen_prob], 1).cpu()
     ne = emo_prob.shape[1]
