@@ -165,3 +165,27 @@ def test_corpus_scale_properties(ex):
     blk = ex.split_band_major(m, mlay, 120)[u].cpu().numpy()
     refm = restate.mfcc(wav[off[u]:off[u + 1]][None], dtype=np.float64)[0]
     assert np.max(np.abs(blk - refm)) / np.max(np.abs(refm)) < TOL_MFCC_REL
+
+
+def test_other_hops_and_mel_counts_fuzz(ex):
+    """Parameters the reference never uses but the C ABI accepts: every combination is checked against the fp64 oracle."""
+    from speech_emotion_privacy_trust_b200 import synth
+    rng = np.random.default_rng(2026)
+    combos = [(800, 80, 23), (800, 320, 256), (800, 400, 80), (1600, 100, 64), (1600, 480, 128), (400, 80, 40),
+              (400, 160, 128), (400, 400, 96), (800, 160, 1), (1600, 160, 33)]
+    for n_fft, hop, n_mels in combos:
+        lens = [int(n_fft // 2 + 1 + rng.integers(0, 3 * n_fft)) for _ in range(5)] + [n_fft // 2 + 1, 5 * hop, 5 * hop - 1]
+        lens = [max(n, n_fft // 2 + 1) for n in lens]
+        waves = [synth.speech_shaped(n, rng) for n in lens]
+        batch = ex.RaggedAudio.from_list(waves)
+        fm, lay = ex.logmel(batch, n_fft=n_fft, n_mels=n_mels, hop=hop)
+        fo = lay.frame_off_host
+        fb = restate.melscale_fbanks_htk(n_fft // 2 + 1, n_mels)
+        for u, w in enumerate(waves):
+            ref = restate.amplitude_to_db_power((restate.power_spectrogram(w, n_fft, hop, np.float64).T @ fb).T)
+            got = fm[fo[u]:fo[u + 1]].cpu().numpy().T
+            assert got.shape == ref.shape == (n_mels, 1 + len(w) // hop), (n_fft, hop, n_mels, u)
+            e_strong, e_all = logmel_error(got, ref)
+            assert e_strong < TOL_DB and e_all < TOL_DB_FLOOR, (n_fft, hop, n_mels, u, e_strong, e_all)
+    with pytest.raises(ValueError, match="hop"):
+        ex.logmel(ex.RaggedAudio.from_list([np.zeros(4000, np.float32)]), n_fft=800, hop=161)
