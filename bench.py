@@ -366,8 +366,9 @@ def secondary_metrics(args, dev, rank, world, batch=None, hours=None):
         out["cloak_eval"] = eval_throughput(dev)
         out["cloak_kernels"] = cloak_kernel_bandwidth(dev)
         if world == 1:
-            from benchmarks_train import train_cpu_baseline
+            from benchmarks_train import eval_cpu_baseline, train_cpu_baseline
             out["train_cpu_baseline"] = train_cpu_baseline()
+            out["cloak_eval_cpu_baseline"] = eval_cpu_baseline()
     if batch is not None:
         out["other_features_this_rank"] = other_features(batch, hours, dev)
     return out

@@ -196,3 +196,24 @@ def train_cpu_baseline(batch=32, steps=2, warmup=1):
     dt = (time.perf_counter() - t0) / steps
     return {"value": batch / dt, "unit": "utterances/s", "cores": threads, "kind": "port", "ms_per_step": dt * 1e3,
             "sample": f"{steps} steps of B={batch} after {warmup} warm-up, reference-style step (oracle/train_port.py)"}
+
+
+def eval_cpu_baseline(n_utts=4, seed=8):
+    """The reference's evaluation loop on the host cores (oracle/train_port.evaluate_utterance: batch 1 per window),
+    windows/s on a bounded sample of synthetic test utterances."""
+    import os
+    import time
+    from oracle import train_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    noise = train_port.CloakNoise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 5.0, "cpu")
+    base, adv = train_port.Classifier("emotion").eval(), train_port.Classifier("gender").eval()
+    feats = [torch.randn(int(rng.integers(201, 1002)), 128) for _ in range(n_utts)]
+    train_port.evaluate_utterance(noise, base, adv, feats[0][:250])
+    t0 = time.perf_counter()
+    n_win = sum(train_port.evaluate_utterance(noise, base, adv, f)[2] for f in feats)
+    dt = time.perf_counter() - t0
+    return {"value": n_win / dt, "unit": "windows/s", "cores": threads, "kind": "port",
+            "sample": f"{n_utts} utterances, {n_win} windows, batch 1 per window (oracle/train_port.py)"}

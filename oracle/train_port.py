@@ -133,3 +133,19 @@ def build(device="cpu", grl_lambda=0.1, seed=8, min_scale=0.01, max_scale=10.0):
     torch.manual_seed(seed)
     noise = CloakNoise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), min_scale, max_scale, device)
     return CloakGRLModel(Classifier("emotion"), Classifier("gender"), noise, grl_lambda).to(device)
+
+
+@torch.no_grad()
+def evaluate_utterance(noise_model: CloakNoise, baseline_model: Classifier, adversary_model: Classifier, feat, device="cpu",
+                       mask=None, win_len=200, shift_len=50):
+    """The per-utterance body of adversary_cloak_evaluation.test() (:69-93): batch 1, one window at a time, two softmax
+    rows copied to the host per window, mean + argmax.  feat: (T, 128) normalised features, T >= win_len."""
+    import numpy as np
+    sm = nn.Softmax(dim=1)
+    pe, pg = [], []
+    for i in range(int((feat.shape[0] - win_len) / shift_len) + 1):
+        x = feat[None, None, i * shift_len:i * shift_len + win_len, :].to(device)
+        noisy = noise_model(x.float(), mask).detach()
+        pe.append(sm(baseline_model.head(baseline_model.features(noisy), "emotion")).cpu().numpy()[0])
+        pg.append(sm(adversary_model.head(adversary_model.features(noisy), "gender")).cpu().numpy()[0])
+    return int(np.argmax(np.mean(np.array(pe), axis=0))), int(np.argmax(np.mean(np.array(pg), axis=0))), len(pe)
