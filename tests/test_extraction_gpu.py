@@ -189,3 +189,29 @@ def test_other_hops_and_mel_counts_fuzz(ex):
             assert e_strong < TOL_DB and e_all < TOL_DB_FLOOR, (n_fft, hop, n_mels, u, e_strong, e_all)
     with pytest.raises(ValueError, match="hop"):
         ex.logmel(ex.RaggedAudio.from_list([np.zeros(4000, np.float32)]), n_fft=800, hop=161)
+
+
+def test_against_reference_port_at_corpus_lengths(ex):
+    """2-10 s utterances (the corpus shape of BASELINE.json configs[0]) against oracle/ref_port.py -- the reference's own
+    callables restated on torchaudio, bit-identical to the reference on the golden vectors -- run on the host CPU."""
+    from oracle import ref_port
+    from speech_emotion_privacy_trust_b200 import synth
+    torch.set_num_threads(4)
+    wav, off = synth.corpus(12, seed=77)
+    batch = ex.RaggedAudio(torch.from_numpy(wav).cuda(), off)
+    m1, lay = ex.logmel(batch, n_fft=800, band_major=True)
+    m2, _ = ex.logmel(batch, n_fft=1600, band_major=True)
+    mf, mlay = ex.mfcc(batch)
+    b1, b2, bm = ex.split_band_major(m1, lay, 128), ex.split_band_major(m2, lay, 128), ex.split_band_major(mf, mlay, 120)
+    for u in range(12):
+        a = torch.from_numpy(wav[off[u]:off[u + 1]])[None]
+        for got, ref in ((b1[u], ref_port.mel_spectrogram(a, 800, 128)[0]), (b2[u], ref_port.mel_spectrogram(a, 1600, 128)[0])):
+            got, ref = got.cpu().numpy(), ref.numpy()
+            assert got.shape == ref.shape
+            strong = ref > ref.max(axis=0, keepdims=True) - 50.0
+            assert np.max(np.abs(got - ref)[strong]) < TOL_DB          # both sides fp32: compare where the signal is
+            assert np.max(np.abs(got - ref)) < 2 * TOL_DB_FLOOR
+        ref = ref_port.mfcc(a)[0]
+        got = bm[u].cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < TOL_MFCC_REL
