@@ -44,15 +44,18 @@ def library_path() -> Path:
 
 
 def lib() -> C.CDLL:
-    """Load (building first if the .so is absent or stale and nvcc exists).  Raises if neither is possible."""
+    """Load libsept_b200.so; build it first (under a file lock: several ranks may start together) only if it is absent.
+    A stale library is rebuilt by `python -m speech_emotion_privacy_trust_b200.build` / __graft_entry__.build(), never
+    implicitly.  Raises if the library is missing and cannot be built -- there is no CPU fallback."""
     global _LIB
     if _LIB is None:
         path = _build.LIB
-        try:
-            path = _build.build()
-        except RuntimeError:
-            if not path.exists():
-                raise
+        if not path.exists():
+            import fcntl
+            with open(str(path) + ".lock", "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                if not path.exists():
+                    _build.build()
         handle = C.CDLL(str(path))
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)

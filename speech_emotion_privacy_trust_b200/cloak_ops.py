@@ -5,7 +5,7 @@ import torch
 
 from . import _lib
 
-_WORKSPACES: dict[tuple[int, int], torch.Tensor] = {}
+_WORKSPACES: dict[tuple[int, int, int], torch.Tensor] = {}
 
 
 def _stream(device) -> int:
@@ -13,7 +13,9 @@ def _stream(device) -> int:
 
 
 def _workspace(device: torch.device, wf: int) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), wf)
+    """Partial-sum buffer + counters of the backward kernel, one per (device, W*F, stream): launches on different
+    streams must not share it."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), wf, _stream(device))
     ws = _WORKSPACES.get(key)
     if ws is None:
         nbytes = _lib.lib().sept_cloak_bwd_workspace_bytes(wf)

@@ -141,17 +141,6 @@ def split_band_major(flat: torch.Tensor, lay: Layout, rows: int) -> list[torch.T
 
 
 # ---- host-buffer entry point: copies pipelined against the kernel ----------------------------------------------
-_PINNED: dict[tuple[str, int], torch.Tensor] = {}
-
-
-def _pinned_i64(tag: str, n: int) -> torch.Tensor:
-    t = _PINNED.get((tag, 0))
-    if t is None or t.numel() < n:
-        t = torch.empty(max(n, 1024), dtype=torch.int64, pin_memory=True)
-        _PINNED[(tag, 0)] = t
-    return t[:n]
-
-
 def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 800, n_mels: int = 128, hop: int = HOP_MEL,
                 out_host: torch.Tensor | None = None, device="cuda", chunk_samples: int = 1 << 25, n_streams: int = 3):
     """log-mel dB for a ragged batch that lives in HOST memory, result back in host memory (frame-major).
@@ -182,7 +171,8 @@ def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 8
     # all per-chunk offset tables in one pinned buffer, one H2D copy
     per = [(bounds[c], bounds[c + 1]) for c in range(n_chunks)]
     words = sum(3 * (b - a + 1) for a, b in per)
-    tab_host = _pinned_i64("tab", words)
+    tab_host = torch.empty(words, dtype=torch.int64, pin_memory=True)   # torch's pinned allocator is stream aware: the
+                                                                        # block is not reused before the copy below has run
     pos, slots = 0, []
     for a, b in per:
         k = b - a + 1
