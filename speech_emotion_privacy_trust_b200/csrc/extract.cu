@@ -106,8 +106,8 @@ __device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const f4* mel
     }
 }
 
-template <int R, int MODE, int WMAX>
-__global__ void __launch_bounds__(WMAX * 32, 1) extract_kernel(const ExtractParams prm) {
+template <int R, int MODE>
+__global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel(const ExtractParams prm) {
     using G = Geo<R>;
     const int kExtractWarps = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -340,12 +340,10 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
 // ---- host launchers ----------------------------------------------------------------------------------------
 constexpr size_t kMaxSmem = 232448;      // 227 KB opt-in limit per CTA
 
-// tuning knob (bench experiments only): SEPT_EXTRACT_WARPS overrides the default warp count (<= 8 selects the
-// 255-register build of the kernel, more the 168-register one)
-static int warp_cap(int r_default, int r_max) {
+// tuning knob (bench experiments only): SEPT_EXTRACT_WARPS lowers the warp count (occupancy-scaling measurements)
+static int warp_cap(int r_max) {
     static const int env = [] { const char* e = getenv("SEPT_EXTRACT_WARPS"); return e ? atoi(e) : 0; }();
-    const int w = env > 0 ? env : r_default;
-    return w < r_max ? w : r_max;
+    return (env > 0 && env < r_max) ? env : r_max;
 }
 
 template <int R>
@@ -354,7 +352,7 @@ static int extract_warps(int hop, int n_wquads, int n_mels) {     // warps whose
     const size_t cb = (size_t)extract_const_bytes(R, n_wquads, n_mels), wb = G::stage_floats(hop) * 4 + G::Y_PK4 * 16;
     if (cb + wb > kMaxSmem) return 0;
     const int fit = (int)((kMaxSmem - cb) / wb);
-    const int cap = warp_cap(ExtractWarpsDefault<R>::value, ExtractWarps<R>::value);
+    const int cap = warp_cap(ExtractWarps<R>::value);
     return fit < cap ? fit : cap;
 }
 
@@ -370,7 +368,7 @@ template <int R, int MODE>
 static cudaError_t launch_one(const ExtractParams& prm, int grid, cudaStream_t stream) {
     const size_t smem = extract_smem_bytes<R>(prm.hop, prm.n_wquads, prm.n_mels);
     const int warps = extract_warps<R>(prm.hop, prm.n_wquads, prm.n_mels);
-    auto kern = warps <= 8 ? extract_kernel<R, MODE, 8> : extract_kernel<R, MODE, ExtractWarps<R>::value>;
+    auto kern = extract_kernel<R, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, stream>>>(prm);

@@ -13,10 +13,10 @@ enum : int {
                              // s = 0 (waveform) and s = 1 (np.gradient of it) + per-utterance max into utt_max
 };
 
-// warps per CTA (one persistent CTA per SM); bounded by the 227 KB of shared memory the warp tiles take
-template <int R> struct ExtractWarps { static constexpr int value = (R == 16) ? 11 : 10; };   // upper bound of the many-warp build
-// default warps per CTA: the fused pass-2 + split of R <= 16 wants ~200 registers, so 8 warps (255 registers) beat 11 (168 + spills)
-template <int R> struct ExtractWarpsDefault { static constexpr int value = 8; };
+// warps per CTA (one persistent CTA per SM).  8 warps = 2 per scheduler = 255 registers per thread: the fused pass 2 +
+// split keeps two spectrum rows of a frame pair in registers (~200); 11 warps would fit the 227 KB of shared memory but
+// leave 168 registers, and the spills cost more than the extra warps give (measured 4.55 ms vs 3.94 ms per step).
+template <int R> struct ExtractWarps { static constexpr int value = 8; };
 
 struct ExtractParams {
     const float* wav;            // all utterances back to back
