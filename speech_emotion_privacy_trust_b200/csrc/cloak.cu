@@ -80,13 +80,31 @@ __global__ void __launch_bounds__(kCloakThreads) cloak_fwd_kernel(const CloakFwd
         nz = cloak_noise4(p, mu, rho, e, m);
         if (p.noise_out && blockIdx.y == 0) st4(p.noise_out + i, nz);
     }
+    if (!p.per_sample) {
+        // shared eps: four batch rows per trip, all loads issued before the first store (the kernel is latency bound:
+        // 13 MB per launch is ~2 us of HBM time)
+        const int step = gridDim.y;
+        for (int b = blockIdx.y; b < p.batch; b += 4 * step) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (b + j * step < p.batch) v[j] = __ldcs(reinterpret_cast<const float4*>(p.x + (size_t)(b + j * step) * p.wf + i));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (b + j * step >= p.batch) break;
+                float4 t = v[j];
+                if (p.mask) { t.x = __fmul_rn(t.x, m.x); t.y = __fmul_rn(t.y, m.y); t.z = __fmul_rn(t.z, m.z); t.w = __fmul_rn(t.w, m.w); }
+                t.x = __fadd_rn(t.x, nz.x); t.y = __fadd_rn(t.y, nz.y); t.z = __fadd_rn(t.z, nz.z); t.w = __fadd_rn(t.w, nz.w);
+                st4(p.out + (size_t)(b + j * step) * p.wf + i, t);
+            }
+        }
+        return;
+    }
     for (int b = blockIdx.y; b < p.batch; b += gridDim.y) {
         const size_t o = (size_t)b * p.wf + i;
-        if (p.per_sample) {
-            const float4 e = p.eps ? ld4(p.eps + o) : normal4(p.seed, off + (uint64_t)b * quads, (uint32_t)i4, p.eps_std);
-            if (p.eps_out) st4(p.eps_out + o, e);
-            nz = cloak_noise4(p, mu, rho, e, m);
-        }
+        const float4 e = p.eps ? ld4(p.eps + o) : normal4(p.seed, off + (uint64_t)b * quads, (uint32_t)i4, p.eps_std);
+        if (p.eps_out) st4(p.eps_out + o, e);
+        nz = cloak_noise4(p, mu, rho, e, m);
         float4 v = ld4(p.x + o);
         if (p.mask) { v.x = __fmul_rn(v.x, m.x); v.y = __fmul_rn(v.y, m.y); v.z = __fmul_rn(v.z, m.z); v.w = __fmul_rn(v.w, m.w); }
         v.x = __fadd_rn(v.x, nz.x); v.y = __fadd_rn(v.y, nz.y); v.z = __fadd_rn(v.z, nz.z); v.w = __fadd_rn(v.w, nz.w);
@@ -102,15 +120,25 @@ __global__ void __launch_bounds__(kCloakThreads) cloak_bwd_kernel(const CloakBwd
     if (live && p.mask) m = ld4(p.mask + i);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
-        for (int b = blockIdx.y; b < p.batch; b += gridDim.y) {
-            const size_t o = (size_t)b * p.wf + i;
-            float4 g = ld4(p.g_a + o);
-            if (p.g_b) {
-                const float4 h = ld4(p.g_b + o);
-                g.x -= p.lambda * h.x; g.y -= p.lambda * h.y; g.z -= p.lambda * h.z; g.w -= p.lambda * h.w;
+        const int step = gridDim.y;
+        for (int b = blockIdx.y; b < p.batch; b += 4 * step) {     // four batch rows (eight loads) in flight per thread
+            float4 ga[4], gb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool on = b + j * step < p.batch;
+                const size_t o = (size_t)(b + j * step) * p.wf + i;
+                ga[j] = on ? __ldcs(reinterpret_cast<const float4*>(p.g_a + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                gb[j] = (on && p.g_b) ? __ldcs(reinterpret_cast<const float4*>(p.g_b + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
-            if (p.dx) st4(p.dx + o, make_float4(g.x * m.x, g.y * m.y, g.z * m.z, g.w * m.w));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (b + j * step >= p.batch) break;
+                float4 g = ga[j];
+                const float4 h = gb[j];
+                g.x -= p.lambda * h.x; g.y -= p.lambda * h.y; g.z -= p.lambda * h.z; g.w -= p.lambda * h.w;
+                s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+                if (p.dx) st4(p.dx + (size_t)(b + j * step) * p.wf + i, make_float4(g.x * m.x, g.y * m.y, g.z * m.z, g.w * m.w));
+            }
         }
         st4(p.partial + (size_t)blockIdx.y * p.wf + i, s);
     }
