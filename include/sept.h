@@ -8,7 +8,7 @@
  * Conventions
  *   - every pointer named *_dev is DEVICE memory owned by the caller (e.g. a torch tensor's data_ptr); every buffer is
  *     allocated by the caller; the library owns only an immutable per-device cache of constants (Hann window, split
- *     twiddles, mel tap lists, DCT basis) created on first use or by sept_init().
+ *     twiddles, mel band weights, DCT basis, resampling rows) created on first use or by sept_init().
  *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); calls enqueue work and return; after
  *     sept_init() they neither allocate nor synchronise, so they can be captured into CUDA graphs.
  *   - return value: 0 on success, a negative SEPT_E_* code otherwise; sept_last_error() gives the text (thread local).
