@@ -90,6 +90,10 @@ int sept_resample_layout(const int64_t* in_off_host, int n_utts, int orig_freq, 
 int sept_resample_f32(const float* in_dev, const int64_t* in_off_dev, const int64_t* out_off_dev, int n_utts,
                       int64_t total_out, int orig_freq, int new_freq, float* out_dev, sept_stream_t stream);
 
+/* 16-bit PCM -> float32 in [-1, 1): out = pcm / 32768, the normalisation torchaudio.load applies before the reference's
+ * callables see the audio (feature_extraction/audio_feature_extraction.py:182); lets bulk jobs copy half the bytes. */
+int sept_pcm16_to_f32(const int16_t* pcm_dev, int64_t n, float* out_dev, sept_stream_t stream);
+
 /* ---- per-speaker normalisation (preprocess_data/preprocess_adversary_data.py:26-27, 41-48, 357-385) -------------
  * feat_dev: (total_frames, n_feat) frame-major features; a frame that lies in k training windows (win_len, shift_len)
  * counts k times, utterances flagged in whole_dev (test split) count every frame once.

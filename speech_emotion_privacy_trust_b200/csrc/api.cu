@@ -282,6 +282,13 @@ int sept_resample_f32(const float* in, const int64_t* in_off, const int64_t* out
     return SEPT_OK;
 }
 
+int sept_pcm16_to_f32(const int16_t* pcm, int64_t n, float* out, sept_stream_t stream) {
+    if (n == 0) return SEPT_OK;
+    if (!pcm || !out || n < 0) return fail(SEPT_E_BADARG, "sept_pcm16_to_f32: bad argument");
+    SEPT_CUDA(sept::launch_pcm16_to_f32(pcm, n, out, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
 int sept_speaker_stats_f32(const float* feat, const int64_t* frame_off, const uint8_t* whole, int n_utts, int n_feat,
                            int win_len, int shift_len, const int32_t* spk_ptr, const int32_t* spk_utts, int n_spk,
                            float* utt_partial, float* stats, sept_stream_t stream) {

@@ -57,6 +57,21 @@ __global__ void __launch_bounds__(kResampleThreads) resample_kernel(const Resamp
     p.out[g] = acc;
 }
 
+// 16-bit PCM -> float in [-1, 1): x / 32768, what torchaudio.load(normalize=True) does on the host before the reference's
+// callables see the audio (audio_feature_extraction.py:182).  Lets a bulk job ship half the bytes over PCIe.
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const short* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i] * (1.0f / 32768.0f);
+}
+
+cudaError_t launch_pcm16_to_f32(const short* in, long long n, float* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pcm16_to_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resample(const ResampleParams& p, cudaStream_t stream) {
     if (p.total_out <= 0) return cudaSuccess;
     const long long blocks = (p.total_out + kResampleThreads - 1) / kResampleThreads;

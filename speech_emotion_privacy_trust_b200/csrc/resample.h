@@ -20,5 +20,6 @@ struct ResampleParams {
 };
 
 cudaError_t launch_resample(const ResampleParams& p, cudaStream_t stream);
+cudaError_t launch_pcm16_to_f32(const short* in, long long n, float* out, cudaStream_t stream);
 
 }  // namespace sept

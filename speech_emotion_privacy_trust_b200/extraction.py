@@ -145,13 +145,16 @@ def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 8
                 out_host: torch.Tensor | None = None, device="cuda", chunk_samples: int = 1 << 25, n_streams: int = 3):
     """log-mel dB for a ragged batch that lives in HOST memory, result back in host memory (frame-major).
 
+    wav_host may also be 16-bit PCM (int16): it is converted on the device as x / 32768, exactly what torchaudio.load does
+    on the host before the reference's callables see the audio, and halves the host->device bytes.
     The batch is cut into chunks of about `chunk_samples` samples at utterance boundaries; each chunk is copied to the
     device, extracted and copied back on one of `n_streams` streams, so the H2D copy, the kernel and the D2H copy of
     neighbouring chunks overlap (PCIe is full duplex).  Pass pinned tensors to get asynchronous copies.
     Returns (out_host, frame_off_host)."""
     dev = torch.device(device)
-    if wav_host.is_cuda or wav_host.dtype != torch.float32 or wav_host.dim() != 1:
-        raise ValueError("wav_host must be a 1-D float32 host tensor")
+    if wav_host.is_cuda or wav_host.dtype not in (torch.float32, torch.int16) or wav_host.dim() != 1:
+        raise ValueError("wav_host must be a 1-D float32 (or 16-bit PCM int16) host tensor")
+    pcm16 = wav_host.dtype == torch.int16
     lib = _lib.lib()
     off = np.ascontiguousarray(utt_off_host, dtype=np.int64)
     n = len(off) - 1
@@ -189,6 +192,7 @@ def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 8
         streams = [torch.cuda.Stream(dev) for _ in range(min(n_streams, n_chunks))]
         bufs = [(torch.empty(max_samples, dtype=torch.float32, device=dev),
                  torch.empty((max_frames, n_mels), dtype=torch.float32, device=dev)) for _ in streams]
+        pcm_bufs = [torch.empty(max_samples, dtype=torch.int16, device=dev) for _ in streams] if pcm16 else None
         ready = torch.cuda.Event()
         ready.record(main)
         for c, (a, b) in enumerate(per):
@@ -199,7 +203,12 @@ def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 8
             with torch.cuda.stream(s):
                 if c < len(streams):
                     s.wait_event(ready)
-                wbuf[:ns].copy_(wav_host[off[a]:off[b]], non_blocking=True)
+                if pcm16:
+                    pbuf = pcm_bufs[c % len(streams)]
+                    pbuf[:ns].copy_(wav_host[int(off[a]):int(off[b])], non_blocking=True)
+                    _lib.check(lib.sept_pcm16_to_f32(pbuf.data_ptr(), ns, wbuf.data_ptr(), s.cuda_stream))
+                else:
+                    wbuf[:ns].copy_(wav_host[int(off[a]):int(off[b])], non_blocking=True)
                 base = tab_dev.data_ptr() + 8 * p
                 _lib.check(lib.sept_logmel_f32(wbuf.data_ptr(), base, base + 8 * k, base + 16 * k, b - a, n_fft, hop, n_mels,
                                                0, 0, obuf.data_ptr(), s.cuda_stream))
@@ -209,4 +218,6 @@ def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 8
         for wbuf, obuf in bufs:
             wbuf.record_stream(main)
             obuf.record_stream(main)
+        for pbuf in pcm_bufs or []:
+            pbuf.record_stream(main)
     return out_host, frame_off

@@ -215,3 +215,18 @@ def test_against_reference_port_at_corpus_lengths(ex):
         got = bm[u].cpu().numpy()
         assert got.shape == ref.shape
         assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < TOL_MFCC_REL
+
+
+def test_host_buffer_api_float_and_pcm16(ex):
+    """extraction.logmel_host: chunked H2D / kernel / D2H pipeline equals the device-resident call bit for bit, for
+    float32 input and for 16-bit PCM input (x / 32768 on the device == torchaudio.load's normalisation on the host)."""
+    from speech_emotion_privacy_trust_b200 import synth
+    wav, off = synth.corpus(40, seed=5, lo_s=0.5, hi_s=3.0)
+    pcm = np.round(wav * 32767.0).astype(np.int16)
+    wav_q = pcm.astype(np.float32) / 32768.0                      # what torchaudio.load(normalize=True) returns
+    ref, lay = ex.logmel(ex.RaggedAudio(torch.from_numpy(wav_q).cuda(), off), n_fft=800)
+    for host, tag in ((torch.from_numpy(wav_q).pin_memory(), "float32"), (torch.from_numpy(pcm).pin_memory(), "pcm16")):
+        out, fo = ex.logmel_host(host, off, n_fft=800, chunk_samples=1 << 18, n_streams=3)     # 5+ chunks
+        torch.cuda.synchronize()
+        assert np.array_equal(fo, lay.frame_off_host), tag
+        assert torch.equal(out, ref.cpu()), tag
