@@ -50,7 +50,8 @@ def lib() -> C.CDLL:
     implicitly.  Raises if the library is missing and cannot be built -- there is no CPU fallback."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB
+        import os
+        path = Path(os.environ["SEPT_LIB_PATH"]) if os.environ.get("SEPT_LIB_PATH") else _build.LIB   # experiments only
         if not path.exists():
             import fcntl
             with open(str(path) + ".lock", "w") as lock:
