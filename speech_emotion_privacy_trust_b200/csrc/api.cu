@@ -47,9 +47,8 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 struct ExtractConsts {
     float* window = nullptr;
     float* tws = nullptr;
-    float* mel_w = nullptr;
-    void* mel_bands = nullptr;
-    int n_wquads = 0;
+    sept::MelStep* mel_prog = nullptr;
+    int n_mel_entries = 0, n_mel_head = 0, mel_fast = 0;
 };
 
 struct ResampleConsts {
@@ -88,16 +87,14 @@ int get_consts(int n_fft, int n_mels, ExtractConsts* out, int* sm_count) {
         ExtractConsts c;
         std::vector<float> win = sept::make_hann_periodic(n_fft);
         std::vector<float> tws = sept::make_split_twiddles(n_fft);
-        std::vector<sept::MelBand> bands;
-        std::vector<float> weights;
-        sept::make_mel_bands(n_fft, n_mels, 16000, bands, weights);
-        c.n_wquads = (int)(weights.size() / 4);
-        sept::MelBand* dbands = nullptr;
+        sept::MelProgram prog;
+        sept::make_mel_program(n_fft, n_mels, 16000, sept::power_tile_pos, prog);
+        c.n_mel_entries = (int)prog.entries.size();
+        c.n_mel_head = prog.n_head;
+        c.mel_fast = sept::extract_mel_fast_ok(n_fft, n_mels, prog.n_head, prog.round_steps.data(), (int)prog.round_steps.size()) ? 1 : 0;
         SEPT_CUDA(upload(win, &c.window));
         SEPT_CUDA(upload(tws, &c.tws));
-        SEPT_CUDA(upload(weights, &c.mel_w));
-        SEPT_CUDA(upload(bands, &dbands));
-        c.mel_bands = dbands;
+        SEPT_CUDA(upload(prog.entries, &c.mel_prog));
         it = g_consts.emplace(key, c).first;
     }
     *out = it->second;
@@ -142,13 +139,13 @@ int get_resample(int orig, int up, ResampleConsts* out) {
 
 bool supported_n_fft(int n_fft) { return n_fft == 400 || n_fft == 800 || n_fft == 1600; }
 
-int check_extract_shape(int n_fft, int hop, int n_mels, int n_wquads) {
+int check_extract_shape(int n_fft, int hop, int n_mels, int n_mel_entries) {
     if (!supported_n_fft(n_fft))
         return fail(SEPT_E_UNSUPPORTED, "n_fft=%d unsupported: the kernels cover 400, 800 and 1600 (2^a * 25)", n_fft);
     if (hop <= 0 || (hop & 1) || hop > n_fft)
         return fail(SEPT_E_UNSUPPORTED, "hop=%d unsupported: must be even and in (0, n_fft]", hop);
     if (n_mels <= 0 || n_mels > 512) return fail(SEPT_E_UNSUPPORTED, "n_mels=%d unsupported (1..512)", n_mels);
-    if (n_wquads >= 0 && sept::extract_smem_bytes_for(n_fft, hop, n_wquads, n_mels) > 232448)
+    if (n_mel_entries >= 0 && sept::extract_smem_bytes_for(n_fft, hop, n_mel_entries) > 232448)
         return fail(SEPT_E_UNSUPPORTED, "n_fft=%d hop=%d n_mels=%d does not fit the 227 KB of shared memory", n_fft, hop,
                     n_mels);
     return SEPT_OK;
@@ -210,12 +207,12 @@ int sept_logmel_f32(const float* wav, const int64_t* utt_off, const int64_t* fra
     int sms = 0;
     rc = get_consts(n_fft, n_mels, &c, &sms);
     if (rc) return rc;
-    rc = check_extract_shape(n_fft, hop, n_mels, c.n_wquads);
+    rc = check_extract_shape(n_fft, hop, n_mels, c.n_mel_entries);
     if (rc) return rc;
     sept::ExtractParams p{};
     p.wav = wav; p.utt_off = utt_off; p.frame_off = frame_off; p.item_off = item_off;
-    p.n_utts = n_utts; p.hop = hop; p.n_mels = n_mels; p.n_wquads = c.n_wquads; p.deriv = deriv ? 1 : 0;
-    p.window = c.window; p.tws = c.tws; p.mel_w = c.mel_w; p.mel_bands = c.mel_bands;
+    p.n_utts = n_utts; p.hop = hop; p.n_mels = n_mels; p.n_mel_entries = c.n_mel_entries; p.n_mel_head = c.n_mel_head; p.mel_fast = c.mel_fast; p.deriv = deriv ? 1 : 0;
+    p.window = c.window; p.tws = c.tws; p.mel_prog = c.mel_prog;
     p.out = out;
     const int mode = layout == SEPT_LAYOUT_FRAME_MAJOR ? sept::kModeDbFrameMajor : sept::kModeDbBandMajor;
     SEPT_CUDA(sept::launch_extract(p, n_fft, mode, sms, static_cast<cudaStream_t>(stream)));
@@ -238,8 +235,8 @@ int sept_mfcc_f32(const float* wav, const int64_t* utt_off, const int64_t* frame
     SEPT_CUDA(cudaMemsetAsync(utt_max, 0, sizeof(int32_t) * 2 * (size_t)n_utts, st));
     sept::ExtractParams p{};
     p.wav = wav; p.utt_off = utt_off; p.frame_off = frame_off; p.item_off = item_off;
-    p.n_utts = n_utts; p.hop = 200; p.n_mels = 128; p.n_wquads = c.n_wquads; p.total_frames = total_frames;
-    p.window = c.window; p.tws = c.tws; p.mel_w = c.mel_w; p.mel_bands = c.mel_bands;
+    p.n_utts = n_utts; p.hop = 200; p.n_mels = 128; p.n_mel_entries = c.n_mel_entries; p.n_mel_head = c.n_mel_head; p.mel_fast = c.mel_fast; p.total_frames = total_frames;
+    p.window = c.window; p.tws = c.tws; p.mel_prog = c.mel_prog;
     p.out = scratch; p.utt_max = utt_max;
     p.frame_utt = reinterpret_cast<int*>(scratch + 2 * (size_t)total_frames * 128);
     SEPT_CUDA(sept::launch_extract(p, 400, sept::kModeMfccPower, sms, st));

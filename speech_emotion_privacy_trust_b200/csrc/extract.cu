@@ -20,9 +20,9 @@ namespace sept {
 constexpr float kDbPerLog2 = 3.01029995663981195f;   // 10*log10(2)
 constexpr float kAmin = 1e-10f;                        // amplitude_to_DB amin (functional.py:390)
 
-// bytes of the CTA-shared constants: split twiddles, mel weight quads, band descriptors, window
-__host__ __device__ inline int extract_const_bytes(int R, int n_wquads, int n_mels) {
-    return (n_wquads * 16 + n_mels * 16 + R * 25 * 8 + 13 * (R + 1) * 8 + 15) & ~15;
+// bytes of the CTA-shared constants: mel gather program, window, split twiddles
+__host__ __device__ inline int extract_const_bytes(int R, int n_mel_entries) {
+    return (n_mel_entries * 16 + R * 25 * 8 + 13 * (R + 1) * 8 + 15) & ~15;
 }
 
 // 10*log10(max(p, 1e-10)) through MUFU.LG2 (abs. error ~1e-6 in log2 => ~1e-5 dB); the clamp keeps the argument normal,
@@ -64,22 +64,32 @@ struct MelJob {
     int T, t0, u, stream;  // frames of the utterance, first frame of the item, utterance, MFCC stream
 };
 
-// mel bands [m_begin, m_end) (multiples of 32) of every frame pair of one item: sparse dot products over the power
-// tile, log, store; lane = band.  Every lane runs every round (the trip count is warp uniform).
+// mel bands of every frame pair of one item: gather program over the power tile (lane = interval, see tables.h), hand
+// the rising sums to the next band, log, store; lane = band in the stores.  Every lane runs every round (the step count
+// is warp uniform).
 template <class G, int MODE>
-__device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const f4* melw, const band_t* bands, int n_mels,
-                                           const ExtractParams& prm, const MelJob& job, int m_begin, int m_end) {
+__device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const mel_step* prog, int n_mels,
+                                           const ExtractParams& prm, const MelJob& job) {
     float vmax = 0.f;
-    for (int m0 = m_begin; m0 < m_end; m0 += 32) {
+    const int width = n_mels < 32 ? n_mels : 32;
+    const mel_step* e = prog + prm.n_mel_head + (lane < width ? lane : width - 1);
+    pk2 carry[G::PPW];                                            // rising sum of the interval below the round's first
+    mel_head<G>(P, prog, prm.n_mel_head, carry);
+    for (int m0 = 0; m0 < n_mels; m0 += 32) {
         const int m = m0 + lane < n_mels ? m0 + lane : n_mels - 1;
         const bool live = m0 + lane < n_mels;
-        pk2 acc[G::PPW];
-        const band_t info = bands[m];
-        mel_band<G>(P, melw, info, __shfl_sync(0xffffffffu, info.nq, 0), acc);
+        const int n_steps = __shfl_sync(0xffffffffu, e->pad, 0);  // the round's first step carries its step count
+        pk2 U[G::PPW], D[G::PPW];
+        mel_round<G>(P, e, n_steps, width, U, D);
+        e += n_steps * width;
 #pragma unroll
         for (int p = 0; p < G::PPW; ++p) {
+            pk2 below = shfl_up(U[p], 1);
+            if (lane == 0) below = carry[p];
+            carry[p] = shfl_lane(U[p], 31);
+            const pk2 acc = below + D[p];
             const int ta = live ? job.t0 + 2 * p : job.T;         // lanes past the last band store nothing
-            const float va = lo(acc[p]), vb = hi(acc[p]);
+            const float va = lo(acc), vb = hi(acc);
             if (MODE == kModeDbFrameMajor) {
                 float* o = prm.out + (job.f0 + ta) * n_mels + m;
                 if (ta < job.T) o[0] = power_to_db(va);
@@ -96,7 +106,7 @@ __device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const f4* mel
         }
     }
     if (MODE == kModeMfccPower) {
-        if (m_begin == 0 && job.stream == 0 && lane < G::FPW && job.t0 + lane < job.T)
+        if (job.stream == 0 && lane < G::FPW && job.t0 + lane < job.T)
             prm.frame_utt[job.f0 + job.t0 + lane] = job.u;        // saves the DCT kernel a search per frame
         // per-utterance max of the mel power (top_db floor, functional.py:393-402); non-negative floats order like
         // their bit patterns
@@ -106,7 +116,55 @@ __device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const f4* mel
     }
 }
 
-template <int R, int MODE>
+// the same for the compiled-in 128-band program (FastMel<R>): no loops, no step-count broadcasts, one 64-bit
+// address per item with immediate offsets for the stores
+template <class G, int MODE>
+__device__ __forceinline__ void mel_fast(int lane, const pk2* P, const mel_step* prog, const ExtractParams& prm,
+                                         const MelJob& job) {
+    using F = FastMel<G::R>;
+    constexpr int PPW = G::PPW;
+    pk2 U[4][PPW], D[4][PPW], carry[PPW];
+    const mel_step* e = prog + F::head + lane;
+    mel_head<G>(P, prog, F::head, carry);
+    mel_round_fixed<G, F::s0>(P, e, U[0], D[0]);
+    mel_round_fixed<G, F::s1>(P, e + F::s0 * 32, U[1], D[1]);
+    mel_round_fixed<G, F::s2>(P, e + (F::s0 + F::s1) * 32, U[2], D[2]);
+    mel_round_fixed<G, F::s3>(P, e + (F::s0 + F::s1 + F::s2) * 32, U[3], D[3]);
+    const int left = job.T - job.t0;                              // frames of the utterance from the item's first on
+    float* o;
+    if (MODE == kModeDbBandMajor) o = prm.out + job.f0 * 128 + (long long)lane * job.T + job.t0;
+    else o = prm.out + ((MODE == kModeMfccPower ? (long long)job.stream * prm.total_frames : 0) + job.f0 + job.t0) * 128 + lane;
+    const int band_stride = 32 * job.T;
+    float vmax = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int p = 0; p < PPW; ++p) {
+            pk2 below = shfl_up(U[r][p], 1);
+            if (r > 0) carry[p] = shfl_lane(U[r - 1][p], 31);    // every lane takes part in the shuffle
+            if (lane == 0) below = carry[p];
+            const pk2 acc = below + D[r][p];
+            float va = lo(acc), vb = hi(acc);
+            if (MODE == kModeMfccPower) { if (2 * p < left) vmax = fmaxf(vmax, va); if (2 * p + 1 < left) vmax = fmaxf(vmax, vb); }
+            else { va = power_to_db(va); vb = power_to_db(vb); }
+            if (MODE == kModeDbBandMajor) {
+                if (2 * p < left) o[r * band_stride + 2 * p] = va;
+                if (2 * p + 1 < left) o[r * band_stride + 2 * p + 1] = vb;
+            } else {
+                if (2 * p < left) o[(2 * p) * 128 + 32 * r] = va;
+                if (2 * p + 1 < left) o[(2 * p + 1) * 128 + 32 * r] = vb;
+            }
+        }
+    }
+    if (MODE == kModeMfccPower) {
+        if (job.stream == 0 && lane < G::FPW && lane < left) prm.frame_utt[job.f0 + job.t0 + lane] = job.u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+        if (lane == 0) atomicMax(prm.utt_max + (long long)job.stream * prm.n_utts + job.u, __float_as_int(vmax));
+    }
+}
+
+template <int R, int MODE, bool FAST>
 __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel(const ExtractParams prm) {
     using G = Geo<R>;
     const int kExtractWarps = blockDim.x >> 5;
@@ -116,14 +174,13 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     const int stage_floats = G::stage_floats(hop);
 
     // ---- CTA-shared constants -----------------------------------------------------------------------------
-    f4* melw = reinterpret_cast<f4*>(smem_raw);                                  // [n_wquads]
-    band_t* bands = reinterpret_cast<band_t*>(melw + prm.n_wquads);              // [n_mels]
-    f2* win2 = reinterpret_cast<f2*>(bands + n_mels);                            // [NC]
+    mel_step* melp = reinterpret_cast<mel_step*>(smem_raw);                      // [n_mel_entries]
+    f2* win2 = reinterpret_cast<f2*>(melp + prm.n_mel_entries);                  // [NC]
     f2* tws = win2 + G::NC;                                                      // [13][R + 1]
-    const int const_bytes = extract_const_bytes(R, prm.n_wquads, n_mels);
+    const int const_bytes = extract_const_bytes(R, prm.n_mel_entries);
     for (int i = threadIdx.x; i < 13 * G::TWS; i += blockDim.x) tws[i] = reinterpret_cast<const f2*>(prm.tws)[i];
-    for (int i = threadIdx.x; i < prm.n_wquads; i += blockDim.x) melw[i] = reinterpret_cast<const f4*>(prm.mel_w)[i];
-    for (int i = threadIdx.x; i < n_mels; i += blockDim.x) bands[i] = reinterpret_cast<const band_t*>(prm.mel_bands)[i];
+    for (int i = threadIdx.x; i < prm.n_mel_entries; i += blockDim.x)
+        reinterpret_cast<f4*>(melp)[i] = reinterpret_cast<const f4*>(prm.mel_prog)[i];
     for (int i = threadIdx.x; i < G::NC; i += blockDim.x) win2[i] = reinterpret_cast<const f2*>(prm.window)[i];
     __syncthreads();
 
@@ -225,7 +282,8 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
             // ---- mel bands (lane = band, all frame pairs of the item) + log + store --------------------------
             {
                 const MelJob job{cur.f0, cur.T, cur.t0, cur.u, stream};
-                mel_rounds<G, MODE>(lane, P, melw, bands, n_mels, prm, job, 0, n_mels);
+                if constexpr (FAST) mel_fast<G, MODE>(lane, P, melp, prm, job);
+                else mel_rounds<G, MODE>(lane, P, melp, n_mels, prm, job);
             }
             __syncwarp();                                        // P reads done before the next pass 1 overwrites Y
             if (stream == n_streams - 1) cur = nxt;
@@ -347,9 +405,9 @@ static int warp_cap(int r_max) {
 }
 
 template <int R>
-static int extract_warps(int hop, int n_wquads, int n_mels) {     // warps whose tiles fit beside the constants
+static int extract_warps(int hop, int n_mel_entries) {            // warps whose tiles fit beside the constants
     using G = Geo<R>;
-    const size_t cb = (size_t)extract_const_bytes(R, n_wquads, n_mels), wb = G::stage_floats(hop) * 4 + G::Y_PK4 * 16;
+    const size_t cb = (size_t)extract_const_bytes(R, n_mel_entries), wb = G::stage_floats(hop) * 4 + G::Y_PK4 * 16;
     if (cb + wb > kMaxSmem) return 0;
     const int fit = (int)((kMaxSmem - cb) / wb);
     const int cap = warp_cap(ExtractWarps<R>::value);
@@ -357,18 +415,18 @@ static int extract_warps(int hop, int n_wquads, int n_mels) {     // warps whose
 }
 
 template <int R>
-static size_t extract_smem_bytes(int hop, int n_wquads, int n_mels) {
+static size_t extract_smem_bytes(int hop, int n_mel_entries) {
     using G = Geo<R>;
-    const int w = extract_warps<R>(hop, n_wquads, n_mels);
+    const int w = extract_warps<R>(hop, n_mel_entries);
     if (w == 0) return kMaxSmem + 1;
-    return (size_t)extract_const_bytes(R, n_wquads, n_mels) + (size_t)w * (G::stage_floats(hop) * 4 + G::Y_PK4 * 16);
+    return (size_t)extract_const_bytes(R, n_mel_entries) + (size_t)w * (G::stage_floats(hop) * 4 + G::Y_PK4 * 16);
 }
 
 template <int R, int MODE>
 static cudaError_t launch_one(const ExtractParams& prm, int grid, cudaStream_t stream) {
-    const size_t smem = extract_smem_bytes<R>(prm.hop, prm.n_wquads, prm.n_mels);
-    const int warps = extract_warps<R>(prm.hop, prm.n_wquads, prm.n_mels);
-    auto kern = extract_kernel<R, MODE>;
+    const size_t smem = extract_smem_bytes<R>(prm.hop, prm.n_mel_entries);
+    const int warps = extract_warps<R>(prm.hop, prm.n_mel_entries);
+    auto kern = prm.mel_fast ? extract_kernel<R, MODE, true> : extract_kernel<R, MODE, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, stream>>>(prm);
@@ -403,11 +461,27 @@ int extract_frames_per_item(int n_fft) {
     return 0;
 }
 
-size_t extract_smem_bytes_for(int n_fft, int hop, int n_wquads, int n_mels) {
+template <int R>
+static bool fast_ok(int n_head, const int* st) {
+    using F = FastMel<R>;
+    return n_head == F::head && st[0] == F::s0 && st[1] == F::s1 && st[2] == F::s2 && st[3] == F::s3;
+}
+
+bool extract_mel_fast_ok(int n_fft, int n_mels, int n_head, const int* round_steps, int n_rounds) {
+    if (n_mels != 128 || n_rounds != 4) return false;
     switch (n_fft) {
-        case 400: return extract_smem_bytes<8>(hop, n_wquads, n_mels);
-        case 800: return extract_smem_bytes<16>(hop, n_wquads, n_mels);
-        case 1600: return extract_smem_bytes<32>(hop, n_wquads, n_mels);
+        case 400: return fast_ok<8>(n_head, round_steps);
+        case 800: return fast_ok<16>(n_head, round_steps);
+        case 1600: return fast_ok<32>(n_head, round_steps);
+    }
+    return false;
+}
+
+size_t extract_smem_bytes_for(int n_fft, int hop, int n_mel_entries) {
+    switch (n_fft) {
+        case 400: return extract_smem_bytes<8>(hop, n_mel_entries);
+        case 800: return extract_smem_bytes<16>(hop, n_mel_entries);
+        case 1600: return extract_smem_bytes<32>(hop, n_mel_entries);
     }
     return 0;
 }

@@ -26,13 +26,14 @@ struct ExtractParams {
     int n_utts;
     int hop;
     int n_mels;
-    int n_wquads;                // float4 groups of mel weights
+    int n_mel_entries;           // 16-byte entries of the mel gather program (head + steps x width)
+    int n_mel_head;              // broadcast entries of interval 0 in front of the program
+    int mel_fast;                // the program has the compiled-in step counts of the 128-mel filterbank (extract_mel_fast_ok)
     int deriv;                   // dB modes: 0 waveform, 1 np.gradient(waveform)
     long long total_frames;      // kModeMfccPower only
     const float* window;         // [n_fft] periodic Hann
     const float* tws;            // [13][R][4] split twiddles
-    const float* mel_w;          // [n_wquads][4] mel weights (x 1/4), zero padded band runs
-    const void* mel_bands;       // [n_mels] {int k0, w4, nq, pad}
+    const void* mel_prog;        // [n_mel_entries] {float up, dn; int byte offset, pad} (tables.h: make_mel_program)
     float* out;
     int* utt_max;                // kModeMfccPower: [2][n_utts] float bits, zeroed by the caller
     int* frame_utt;              // kModeMfccPower: [total_frames] utterance of every frame
@@ -51,8 +52,10 @@ struct MfccDctParams {
 };
 
 cudaError_t launch_extract(const ExtractParams& prm, int n_fft, int mode, int grid, cudaStream_t stream);
-size_t extract_smem_bytes_for(int n_fft, int hop, int n_wquads, int n_mels);
+size_t extract_smem_bytes_for(int n_fft, int hop, int n_mel_entries);
 int extract_frames_per_item(int n_fft);
+// true when a 128-band program with these step counts may run the unrolled mel path
+bool extract_mel_fast_ok(int n_fft, int n_mels, int n_head, const int* round_steps, int n_rounds);
 cudaError_t launch_mfcc_dct(const MfccDctParams& prm, cudaStream_t stream);
 
 }  // namespace sept

@@ -194,13 +194,6 @@ SEPT_HD bool split_load(int lane, int k2, const pk2* Y, const f2* tws, pk2& pk_,
     return true;
 }
 
-// zero-weight padding of the last band's run reads bins NC+1 .. NC+3: keep them finite
-template <class G>
-SEPT_HD void zero_tail(pk2* base) {
-#pragma unroll
-    for (int i = 1; i <= 3; ++i) base[G::bin_pos(G::NC + i)] = splat(0.f);
-}
-
 // ---- fused pass 2 + split (R <= 16): task (p, j) transforms rows j and 25-j of pair p over n1 in registers and
 // splits them against each other without another trip through shared memory.  pu[k1] = 4|X|^2 at bin CRT(k1, j),
 // pv[k1] = 4|X|^2 at bin CRT(k1, 25-j).  Row 0 (j = 0) is its own partner: pu holds the whole row and pv[0] the
@@ -242,10 +235,7 @@ SEPT_HD void pass2_split_store(int p, int j, pk2* P, const pk2 (&pu)[G::R], cons
             base[G::bin_pos(kk)] = pv[k1];
         }
     }
-    if (j == 0) {
-        base[G::bin_pos(NC)] = pv[0];
-        zero_tail<G>(base);
-    }
+    if (j == 0) base[G::bin_pos(NC)] = pv[0];
 }
 
 // after EVERY lane holds its 13 conjugate pairs in registers (warp barrier), the Y tile is overwritten by the power
@@ -261,36 +251,74 @@ SEPT_HD void split_store_all(int lane, pk2* P, const pk2 (&a)[13], const pk2 (&b
         if (k2 > 0 || on0) {
             base[G::bin_pos(k)] = a[k2];
             if (k != G::NC - k) base[G::bin_pos(G::NC - k)] = b[k2];   // k = 0 pairs with the Nyquist bin NC; NC/2 is its own partner
-            if (k == 0) zero_tail<G>(base);
         }
         k += Pfa<R>::cK2;
         if (k >= G::NC) k -= G::NC;
     }
 }
 
-// ---- mel: band m of every frame pair of the item: dot product over the band's contiguous bins (MelScale,
-// _transforms.py:417).  info = {first bin (multiple of 4), first weight quad, number of quads}; weights are padded with zeros
-// to whole quads that stay inside bins 0..NC+1 ------------------------------------------------------------------------
-struct alignas(16) band_t { int k0, w4, nq, pad; };
+// ---- mel: one round of the gather program (tables.h: make_mel_program) for one lane.  The lane's interval i yields
+// U = sum of rising weights x power (band i) and D = sum of falling weights x power (band i-1) for every frame pair of
+// the item; e points at the lane's entry of the round's first step, entries of one step are `width` apart.  Replaces
+// MelScale's matmul (_transforms.py:417) -------------------------------------------------------------------------------
+struct alignas(16) mel_step { float up, dn; int off, pad; };
 
-// nq is the quad count of the widest band of the lane's round (uniform over the warp: no divergence); narrower bands
-// carry zero-weight quads up to it (tables.h pads them)
 template <class G>
-SEPT_HD void mel_band(const pk2* P, const f4* w4, band_t info, int nq, pk2 (&acc)[G::PPW]) {
+SEPT_HD void mel_round(const pk2* P, const mel_step* e, int n_steps, int width, pk2 (&U)[G::PPW], pk2 (&D)[G::PPW]) {
 #pragma unroll
-    for (int p = 0; p < G::PPW; ++p) acc[p] = splat(0.f);
+    for (int p = 0; p < G::PPW; ++p) { U[p] = splat(0.f); D[p] = splat(0.f); }
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(P);
 #pragma unroll 2
-    for (int q = 0; q < nq; ++q) {
-        const f4 w = w4[info.w4 + q];
+    for (int s = 0; s < n_steps; ++s) {
+        const mel_step st = e[s * width];
+        const pk2 up = splat(st.up), dn = splat(st.dn);
 #pragma unroll
         for (int p = 0; p < G::PPW; ++p) {
-            const pk2* src = P + p * G::PP + G::bin_pos(info.k0 + 4 * q);    // a quad never straddles a 16-bin block
-            const pk2 b0 = src[0], b1 = src[1], b2 = src[2], b3 = src[3];
-            acc[p] = fma2(b0, splat(w.x), acc[p]);
-            acc[p] = fma2(b1, splat(w.y), acc[p]);
-            acc[p] = fma2(b2, splat(w.z), acc[p]);
-            acc[p] = fma2(b3, splat(w.w), acc[p]);
+            const pk2 v = *reinterpret_cast<const pk2*>(base + st.off + p * (G::PP * 8));
+            U[p] = fma2(v, up, U[p]);
+            D[p] = fma2(v, dn, D[p]);
         }
+    }
+}
+
+// the same with a compile-time step count: fully unrolled, every load of the round can be in flight at once
+template <class G, int N>
+SEPT_HD void mel_round_fixed(const pk2* P, const mel_step* e, pk2 (&U)[G::PPW], pk2 (&D)[G::PPW]) {
+#pragma unroll
+    for (int p = 0; p < G::PPW; ++p) { U[p] = splat(0.f); D[p] = splat(0.f); }
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(P);
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        const mel_step st = e[s * 32];
+        const pk2 up = splat(st.up), dn = splat(st.dn);
+#pragma unroll
+        for (int p = 0; p < G::PPW; ++p) {
+            const pk2 v = *reinterpret_cast<const pk2*>(base + st.off + p * (G::PP * 8));
+            U[p] = fma2(v, up, U[p]);
+            D[p] = fma2(v, dn, D[p]);
+        }
+    }
+}
+
+// step counts of the reference's only filterbank (128 HTK mels, 16 kHz; audio_feature_extraction.py:36,42 and the
+// MFCC melkwargs): head entries, then the four rounds.  The library compares them with the program it builds and
+// falls back to the table-driven loops when they differ.
+template <int R> struct FastMel;
+template <> struct FastMel<8> { static constexpr int head = 0, s0 = 1, s1 = 2, s2 = 2, s3 = 5; };
+template <> struct FastMel<16> { static constexpr int head = 0, s0 = 2, s1 = 3, s2 = 5, s3 = 9; };
+template <> struct FastMel<32> { static constexpr int head = 1, s0 = 3, s1 = 5, s2 = 9, s3 = 17; };
+
+// interval 0 (bins below the first mel point): rising side of band 0, the same for every lane (broadcast reads)
+template <class G>
+SEPT_HD void mel_head(const pk2* P, const mel_step* head, int n_head, pk2 (&U)[G::PPW]) {
+#pragma unroll
+    for (int p = 0; p < G::PPW; ++p) U[p] = splat(0.f);
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(P);
+    for (int s = 0; s < n_head; ++s) {
+        const mel_step st = head[s];
+#pragma unroll
+        for (int p = 0; p < G::PPW; ++p)
+            U[p] = fma2(*reinterpret_cast<const pk2*>(base + st.off + p * (G::PP * 8)), splat(st.up), U[p]);
     }
 }
 

@@ -8,6 +8,7 @@
 //                                                                      (functional.py:518-587, 492-515)
 //   dct     torchaudio.functional.create_dct(40, 128, "ortho")         (functional.py:636-667)
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -48,37 +49,134 @@ inline std::vector<float> make_mel_fbank(int n_freqs, int n_mels, int sample_rat
     return fb;
 }
 
-// mel bands as contiguous bin runs: band m covers bins k0 .. k0 + 4*nq - 1 with weights w[4*w4 ..]; k0 is a multiple
-// of 4, runs are padded with zero weights to whole quads and never reach past bin Nc + 3 (the kernel's power tile keeps
-// bins Nc+1 .. Nc+3 at zero).  Weights carry the 1/4 of the kernel's 4|X|^2 convention.
-struct MelBand { int32_t k0, w4, nq, pad; };
+// ---- mel filterbank as a per-lane gather program -------------------------------------------------------------------
+// The HTK triangles (norm=None) partition the bins into INTERVALS between neighbouring mel points: a bin in interval
+// i (f_pts[i] <= f < f_pts[i+1]) lies on the rising slope of band i and on the falling slope of band i-1 and nowhere
+// else, so   mel[b] = U[b] + D[b+1],   U[i] = sum_{k in interval i} fb[k][i] P[k],   D[i] = sum fb[k][i-1] P[k],
+// and every power value is read ONCE for both of its bands.  The kernel gives interval 1 + 32 r + l to lane l in
+// round r; a round runs for as many steps as its widest interval has bins.  One MelStep = {rising weight, falling
+// weight, byte offset of the bin inside a frame pair's power tile}; rows of `width` entries per step.  Interval 0
+// (only its rising side is used, by band 0) is a short broadcast list in front (`head`).
+// The order in which a lane visits its bins is scheduled so that the 16 lanes of a half warp hit 16 different
+// 8-byte bank pairs in (nearly) every step; slots without a bin carry zero weights and the address of a bin another
+// lane of the half warp reads in that step (a broadcast costs nothing).  Weights carry the 1/4 of the kernel's 4|X|^2.
+// pk2 slot of bin k in a frame pair's power tile (the same function as Geo<R>::bin_pos in extract_core.cuh; hostsim
+// checks that they agree)
+inline int power_tile_pos(int k) { return k + (k >> 4); }
 
-inline void make_mel_bands(int n_fft, int n_mels, int sample_rate, std::vector<MelBand>& bands, std::vector<float>& weights) {
-    const int n_freqs = n_fft / 2 + 1, Nc = n_fft / 2;
-    std::vector<float> fb = make_mel_fbank(n_freqs, n_mels, sample_rate, 0.0, (double)(sample_rate / 2));
-    bands.assign(n_mels, MelBand{0, 0, 0, 0});
-    weights.clear();
-    std::vector<int> lo(n_mels, -1), hi(n_mels, -1);
-    for (int m = 0; m < n_mels; ++m)
-        for (int k = 0; k < n_freqs; ++k)
-            if (fb[(size_t)k * n_mels + m] != 0.f) { if (lo[m] < 0) lo[m] = k; hi[m] = k; }
-    // the kernel gives band m to lane m % 32 in round m / 32 and runs every lane of a round for the round's widest band:
-    // narrower bands are padded with zero-weight quads (their reads must stay inside bins 0 .. Nc + 3)
-    for (int r0 = 0; r0 < n_mels; r0 += 32) {
-        int round_nq = 1;
-        for (int m = r0; m < n_mels && m < r0 + 32; ++m)
-            if (lo[m] >= 0) { const int nq = (hi[m] - (lo[m] & ~3) + 4) / 4; if (nq > round_nq) round_nq = nq; }
-        for (int m = r0; m < n_mels && m < r0 + 32; ++m) {
-            int k0 = lo[m] >= 0 ? (lo[m] & ~3) : 0;                  // quads never straddle the tile's 16-bin blocks
-            if (k0 + 4 * round_nq > Nc + 4) k0 = Nc + 4 - 4 * round_nq;
-            MelBand b{k0, (int32_t)(weights.size() / 4), round_nq, 0};
-            for (int i = 0; i < 4 * round_nq; ++i) {
-                const int k = k0 + i;
-                weights.push_back(k < n_freqs ? fb[(size_t)k * n_mels + m] * 0.25f : 0.f);
-            }
-            bands[m] = b;
+struct MelStep { float up, dn; int32_t off, pad; };   // pad: step count of the round in the entries of its first step
+
+struct MelProgram {
+    std::vector<MelStep> entries;          // [n_head] broadcast entries, then [total_steps][width]
+    std::vector<int> round_steps;          // steps of every round, ceil(n_mels / 32) rounds
+    int n_head = 0, width = 32, total_steps = 0;
+};
+
+template <class PosFn>
+inline void make_mel_program(int n_fft, int n_mels, int sample_rate, PosFn pos, MelProgram& prog) {
+    const int n_freqs = n_fft / 2 + 1;
+    const double f_max = (double)(sample_rate / 2);
+    std::vector<float> fb = make_mel_fbank(n_freqs, n_mels, sample_rate, 0.0, f_max);
+    auto hz2mel = [](double f) { return 2595.0 * std::log10(1.0 + f / 700.0); };
+    std::vector<double> f_pts(n_mels + 2);
+    for (int i = 0; i < n_mels + 2; ++i)
+        f_pts[i] = 700.0 * (std::pow(10.0, hz2mel(f_max) * (double)i / (double)(n_mels + 1) / 2595.0) - 1.0);
+    // bins of every interval: the bands with a non-zero weight at bin k are a subset of {i-1, i} for ONE i; take i from
+    // the weights themselves (robust against rounding at the mel points)
+    std::vector<std::vector<int>> bins(n_mels + 1);
+    for (int k = 0; k < n_freqs; ++k) {
+        int first = -1, last = -1;
+        for (int m = 0; m < n_mels; ++m)
+            if (fb[(size_t)k * n_mels + m] != 0.f) { if (first < 0) first = m; last = m; }
+        if (first < 0) continue;                                     // DC, Nyquist: no band
+        int i;
+        if (last == first + 1) i = last;
+        else {                                                       // one band only: which slope?
+            const double f = f_max * (double)k / (double)(n_freqs - 1);
+            i = f < f_pts[first + 1] ? first : first + 1;
         }
+        bins[i].push_back(k);
     }
+    auto up_w = [&](int k, int i) { return i < n_mels ? 0.25f * fb[(size_t)k * n_mels + i] : 0.f; };
+    auto dn_w = [&](int k, int i) { return i >= 1 ? 0.25f * fb[(size_t)k * n_mels + i - 1] : 0.f; };
+    prog.entries.clear();
+    prog.round_steps.clear();
+    prog.width = n_mels < 32 ? n_mels : 32;
+    for (int k : bins[0]) prog.entries.push_back(MelStep{up_w(k, 0), 0.f, 8 * pos(k), 0});
+    prog.n_head = (int)prog.entries.size();
+    prog.total_steps = 0;
+    const int W = prog.width;
+    for (int r0 = 0; r0 < n_mels; r0 += 32) {
+        std::vector<std::vector<int>> rem(W);
+        int n_steps = 1;
+        for (int l = 0; l < W; ++l)
+            if (r0 + l < n_mels) { rem[l] = bins[1 + r0 + l]; if ((int)rem[l].size() > n_steps) n_steps = (int)rem[l].size(); }
+        for (int s = 0; s < n_steps; ++s) {
+            const int left = n_steps - s;
+            std::vector<int> pick(W, -1);
+            for (int h = 0; h < W; h += 16) {
+                const int h_end = h + 16 < W ? h + 16 : W;
+                int used[16] = {0};
+                // lanes with the least slack choose first
+                std::vector<int> order;
+                for (int l = h; l < h_end; ++l) order.push_back(l);
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                    return left - (int)rem[a].size() < left - (int)rem[b].size();
+                });
+                for (int l : order) {
+                    if (rem[l].empty()) continue;
+                    const int slack = left - (int)rem[l].size();
+                    int best = -1;
+                    for (size_t c = 0; c < rem[l].size(); ++c)
+                        if (!used[pos(rem[l][c]) & 15]) { best = (int)c; break; }
+                    if (best < 0) {
+                        if (slack > 0) continue;                     // wait for a free bank pair
+                        best = 0;
+                        for (size_t c = 1; c < rem[l].size(); ++c)
+                            if (used[pos(rem[l][c]) & 15] < used[pos(rem[l][best]) & 15]) best = (int)c;
+                    }
+                    pick[l] = rem[l][best];
+                    ++used[pos(pick[l]) & 15];
+                    rem[l].erase(rem[l].begin() + best);
+                }
+            }
+            for (int l = 0; l < W; ++l) {
+                if (pick[l] >= 0) {
+                    const int k = pick[l], i = 1 + r0 + l;
+                    prog.entries.push_back(MelStep{up_w(k, i), dn_w(k, i), 8 * pos(k), 0});
+                } else {
+                    int k = 0;                                       // idle slot: ride on a neighbour's read
+                    const int h = l & ~15;
+                    for (int o = h; o < h + 16 && o < W; ++o) if (pick[o] >= 0) { k = pick[o]; break; }
+                    prog.entries.push_back(MelStep{0.f, 0.f, 8 * pos(k), 0});
+                }
+            }
+        }
+        for (int l = 0; l < W; ++l) prog.entries[prog.entries.size() - (size_t)n_steps * W + l].pad = n_steps;
+        prog.round_steps.push_back(n_steps);
+        prog.total_steps += n_steps;
+    }
+}
+
+// shared-memory wavefronts of the program's power-tile gathers for ONE frame pair (8-byte reads: two half warps per
+// step, each costing the largest number of distinct 8-byte words that share a bank pair); lower bound 2 per step
+inline int mel_program_wavefronts(const MelProgram& prog) {
+    int total = 0;
+    const int W = prog.width;
+    for (int s = 0; s < prog.total_steps; ++s)
+        for (int h = 0; h < W; h += 16) {
+            int worst = 0;
+            for (int b = 0; b < 16; ++b) {
+                std::vector<int> words;
+                for (int l = h; l < h + 16 && l < W; ++l) {
+                    const int w = prog.entries[prog.n_head + (size_t)s * W + l].off / 8;
+                    if ((w & 15) == b && std::find(words.begin(), words.end(), w) == words.end()) words.push_back(w);
+                }
+                if ((int)words.size() > worst) worst = (int)words.size();
+            }
+            total += worst;
+        }
+    return total;
 }
 
 // split twiddles W_{n_fft}^{k}, k = CRT(k1, k2) for rows k2 = 0..12, columns k1 = 0..R-1: (cos, -sin) pairs, row

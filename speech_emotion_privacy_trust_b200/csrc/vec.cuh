@@ -51,6 +51,15 @@ SEPT_HD void st_shared(pk2* p, pk2 v) {
 SEPT_HD void st_shared(pk2* p, pk2 v) { *p = v; }
 #endif
 
+// warp shuffles of a packed pair (device only; the host emulation walks lanes explicitly and never calls them)
+#if defined(__CUDA_ARCH__)
+SEPT_HD pk2 shfl_up(pk2 x, int d) { pk2 r; r.v = __shfl_up_sync(0xffffffffu, x.v, d); return r; }
+SEPT_HD pk2 shfl_lane(pk2 x, int l) { pk2 r; r.v = __shfl_sync(0xffffffffu, x.v, l); return r; }
+#else
+SEPT_HD pk2 shfl_up(pk2 x, int) { return x; }
+SEPT_HD pk2 shfl_lane(pk2 x, int) { return x; }
+#endif
+
 SEPT_HD pk2 splat(float c) { return pk(c, c); }
 SEPT_HD pk2 neg(pk2 x) { return splat(0.f) - x; }
 // a - b*c

@@ -18,9 +18,12 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
     const int n = (int)wav.size(), n_fft = G::NFFT;
     const int T = 1 + n / hop;
     std::vector<float> win = make_hann_periodic(n_fft), tws = make_split_twiddles(n_fft);
-    std::vector<MelBand> bands;
-    std::vector<float> weights;
-    make_mel_bands(n_fft, n_mels, 16000, bands, weights);
+    MelProgram prog;
+    make_mel_program(n_fft, n_mels, 16000, power_tile_pos, prog);
+    for (int k = 0; k <= G::NC; ++k)
+        if (power_tile_pos(k) != G::bin_pos(k)) return 4;
+    static_assert(sizeof(MelStep) == sizeof(mel_step), "table entry layout");
+    const mel_step* mprog = reinterpret_cast<const mel_step*>(prog.entries.data());
     std::vector<float> stage(G::stage_floats(hop), 0.f);
     std::vector<pk4> Ybuf(G::Y_PK4 + 1);
     pk2* Yp = reinterpret_cast<pk2*>(Ybuf.data());
@@ -58,15 +61,30 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
                 }
             for (int lane = 0; lane < 32; ++lane) split_store_all<G>(lane, P, a[lane], b[lane], on0[lane]);
         }
-        for (int m = 0; m < n_mels; ++m) {
-            pk2 acc[G::PPW];
-            band_t info{bands[m].k0, bands[m].w4, bands[m].nq, 0};
-            mel_band<G>(P, reinterpret_cast<const f4*>(weights.data()), info, info.nq, acc);
-            for (int p = 0; p < G::PPW; ++p) {
-                const int ta = t0 + 2 * p;
-                if (ta < T) out[(size_t)ta * n_mels + m] = 10.0f * std::log10(std::fmax(lo(acc[p]), 1e-10f));
-                if (ta + 1 < T) out[(size_t)(ta + 1) * n_mels + m] = 10.0f * std::log10(std::fmax(hi(acc[p]), 1e-10f));
+        // mel: interval 0 (head), then rounds of 32 intervals; band b = U[interval b] + D[interval b + 1]
+        {
+            std::vector<pk2> Uall((size_t)(n_mels + 1) * G::PPW), Dall((size_t)(n_mels + 1) * G::PPW);
+            pk2 U[G::PPW], D[G::PPW];
+            mel_head<G>(P, mprog, prog.n_head, U);
+            for (int p = 0; p < G::PPW; ++p) Uall[p] = U[p];
+            const mel_step* e = mprog + prog.n_head;
+            for (size_t r = 0; r < prog.round_steps.size(); ++r) {
+                if (e->pad != prog.round_steps[r]) return 5;
+                for (int lane = 0; lane < prog.width; ++lane) {
+                    const int i = 1 + 32 * (int)r + lane;
+                    if (i > n_mels) break;
+                    mel_round<G>(P, e + lane, prog.round_steps[r], prog.width, U, D);
+                    for (int p = 0; p < G::PPW; ++p) { Uall[(size_t)i * G::PPW + p] = U[p]; Dall[(size_t)i * G::PPW + p] = D[p]; }
+                }
+                e += (size_t)prog.round_steps[r] * prog.width;
             }
+            for (int m = 0; m < n_mels; ++m)
+                for (int p = 0; p < G::PPW; ++p) {
+                    const pk2 acc = Uall[(size_t)m * G::PPW + p] + Dall[(size_t)(m + 1) * G::PPW + p];
+                    const int ta = t0 + 2 * p;
+                    if (ta < T) out[(size_t)ta * n_mels + m] = 10.0f * std::log10(std::fmax(lo(acc), 1e-10f));
+                    if (ta + 1 < T) out[(size_t)(ta + 1) * n_mels + m] = 10.0f * std::log10(std::fmax(hi(acc), 1e-10f));
+                }
         }
     }
     FILE* f = std::fopen(out_path, "wb");
