@@ -88,7 +88,7 @@ int get_consts(int n_fft, int n_mels, ExtractConsts* out, int* sm_count) {
         std::vector<float> win = sept::make_hann_periodic(n_fft);
         std::vector<float> tws = sept::make_split_twiddles(n_fft);
         sept::MelProgram prog;
-        sept::make_mel_program(n_fft, n_mels, 16000, sept::power_tile_pos, prog);
+        sept::make_mel_program(n_fft, n_mels, 16000, prog);
         c.n_mel_entries = (int)prog.entries.size();
         c.n_mel_head = prog.n_head;
         c.mel_fast = sept::extract_mel_fast_ok(n_fft, n_mels, prog.n_head, prog.round_steps.data(), (int)prog.round_steps.size()) ? 1 : 0;

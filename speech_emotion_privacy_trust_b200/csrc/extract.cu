@@ -14,6 +14,7 @@
 
 #include "extract.h"
 #include "extract_core.cuh"
+#include "tmem.cuh"
 
 namespace sept {
 
@@ -116,20 +117,74 @@ __device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const mel_ste
     }
 }
 
-// the same for the compiled-in 128-band program (FastMel<R>): no loops, no step-count broadcasts, one 64-bit
-// address per item with immediate offsets for the stores
-template <class G, int MODE>
-__device__ __forceinline__ void mel_fast(int lane, const pk2* P, const mel_step* prog, const ExtractParams& prm,
-                                         const MelJob& job) {
+// ---- the compiled-in 128-band program (FastMel<R>) from tensor memory -----------------------------------------------
+// TMEM columns of a lane: [0, 2 n) = {rising weight, byte offset} of its n = head + s0 + s1 + s2 + s3 program entries
+// (the falling weight of a bin is 1/4 minus its rising weight: the triangles of neighbouring bands sum to one).
+template <int R> struct TmemMap {
+    using F = FastMel<R>;
+    static constexpr int kMelEntries = F::head + F::s0 + F::s1 + F::s2 + F::s3;
+    static constexpr int kMel = 0, kEnd = 2 * kMelEntries;
+    static constexpr uint32_t kCols = kEnd <= 32 ? 32 : kEnd <= 64 ? 64 : kEnd <= 128 ? 128 : 256;
+};
+
+// one round of N steps whose entries sit in registers mp[2 s] = rising weight, mp[2 s + 1] = byte offset
+template <class G, int N>
+__device__ __forceinline__ void mel_round_regs(const pk2* P, const uint32_t* mp, pk2 (&U)[G::PPW], pk2 (&D)[G::PPW]) {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(P);
+#pragma unroll
+    for (int p = 0; p < G::PPW; ++p) { U[p] = splat(0.f); D[p] = splat(0.f); }
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        const float upw = __uint_as_float(mp[2 * s]);
+        const pk2 up = splat(upw), dn = splat(0.25f - upw);
+#pragma unroll
+        for (int p = 0; p < G::PPW; ++p) {
+            const pk2 v = *reinterpret_cast<const pk2*>(base + mp[2 * s + 1] + p * (G::PP * 8));
+            U[p] = fma2(v, up, U[p]);
+            D[p] = fma2(v, dn, D[p]);
+        }
+    }
+}
+
+// fill the calling warp's TMEM quarter with its lanes' program (every warp does; warps w and w + 4 write the same values)
+template <class G>
+__device__ __forceinline__ void tmem_fill_mel(uint32_t taddr, int lane, const mel_step* prog) {
     using F = FastMel<G::R>;
+    using M = TmemMap<G::R>;
+    uint32_t v[2 * M::kMelEntries];
+#pragma unroll
+    for (int s = 0; s < M::kMelEntries; ++s) {
+        const mel_step st = s < F::head ? prog[s] : prog[F::head + (s - F::head) * 32 + lane];
+        v[2 * s] = __float_as_uint(st.up);
+        v[2 * s + 1] = (uint32_t)st.off;
+    }
+    tmem::st<2 * M::kMelEntries>(taddr + M::kMel, v);
+}
+
+// mel bands, log, store of one item: no loops, no table reads from shared memory, one 64-bit address per item with
+// immediate offsets for the stores
+template <class G, int MODE>
+__device__ __forceinline__ void mel_fast(int lane, const pk2* P, uint32_t taddr, const ExtractParams& prm, const MelJob& job) {
+    using F = FastMel<G::R>;
+    using M = TmemMap<G::R>;
     constexpr int PPW = G::PPW;
+    uint32_t mp[2 * M::kMelEntries];
+    tmem::ld<2 * M::kMelEntries>(taddr + M::kMel, mp);
+    tmem::wait_ld();
     pk2 U[4][PPW], D[4][PPW], carry[PPW];
-    const mel_step* e = prog + F::head + lane;
-    mel_head<G>(P, prog, F::head, carry);
-    mel_round_fixed<G, F::s0>(P, e, U[0], D[0]);
-    mel_round_fixed<G, F::s1>(P, e + F::s0 * 32, U[1], D[1]);
-    mel_round_fixed<G, F::s2>(P, e + (F::s0 + F::s1) * 32, U[2], D[2]);
-    mel_round_fixed<G, F::s3>(P, e + (F::s0 + F::s1 + F::s2) * 32, U[3], D[3]);
+#pragma unroll
+    for (int p = 0; p < PPW; ++p) carry[p] = splat(0.f);
+#pragma unroll
+    for (int s = 0; s < F::head; ++s)                              // interval 0: the same entries in every lane
+#pragma unroll
+        for (int p = 0; p < PPW; ++p)
+            carry[p] = fma2(*reinterpret_cast<const pk2*>(reinterpret_cast<const unsigned char*>(P) + mp[2 * s + 1] + p * (G::PP * 8)),
+                            splat(__uint_as_float(mp[2 * s])), carry[p]);
+    const uint32_t* e = mp + 2 * F::head;
+    mel_round_regs<G, F::s0>(P, e, U[0], D[0]);
+    mel_round_regs<G, F::s1>(P, e + 2 * F::s0, U[1], D[1]);
+    mel_round_regs<G, F::s2>(P, e + 2 * (F::s0 + F::s1), U[2], D[2]);
+    mel_round_regs<G, F::s3>(P, e + 2 * (F::s0 + F::s1 + F::s2), U[3], D[3]);
     const int left = job.T - job.t0;                              // frames of the utterance from the item's first on
     float* o;
     if (MODE == kModeDbBandMajor) o = prm.out + job.f0 * 128 + (long long)lane * job.T + job.t0;
@@ -182,7 +237,20 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     for (int i = threadIdx.x; i < prm.n_mel_entries; i += blockDim.x)
         reinterpret_cast<f4*>(melp)[i] = reinterpret_cast<const f4*>(prm.mel_prog)[i];
     for (int i = threadIdx.x; i < G::NC; i += blockDim.x) win2[i] = reinterpret_cast<const f2*>(prm.window)[i];
+    uint32_t taddr = 0;                                           // this warp's quarter of the CTA's tensor memory
+    __shared__ uint32_t tmem_base;
+    if constexpr (FAST) {
+        if (warp == 0) tmem::alloc(&tmem_base, TmemMap<R>::kCols);
+        tmem::fence_before_sync();
+        __syncthreads();
+        tmem::fence_after_sync();
+        taddr = tmem::quarter_addr(tmem_base, warp, 0);
+        tmem_fill_mel<G>(taddr, lane, melp);
+        tmem::wait_st();
+        tmem::fence_before_sync();
+    }
     __syncthreads();
+    if constexpr (FAST) tmem::fence_after_sync();
 
     // ---- warp-private tiles -------------------------------------------------------------------------------
     const int warp_bytes = stage_floats * 4 + G::Y_PK4 * 16;
@@ -196,8 +264,8 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     const int begin = (int)((long long)n_items * blockIdx.x / gridDim.x);
     const int end = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
     int item = begin + warp;
-    if (item >= end) return;
-    int u = find_utt(prm.item_off, prm.n_utts, item);
+    const bool active = item < end;                               // idle warps still reach the barrier at the end
+    int u = active ? find_utt(prm.item_off, prm.n_utts, item) : 0;
     int u_first = __ldg(prm.item_off + u), u_last = __ldg(prm.item_off + u + 1);
 
     auto locate = [&](int it) {
@@ -220,8 +288,11 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
         cp_async_commit();
     };
 
-    ItemRef cur = locate(item);
-    if (cur.interior) prefetch(cur);
+    ItemRef cur{};
+    if (active) {
+        cur = locate(item);
+        if (cur.interior) prefetch(cur);
+    }
 
     constexpr int n_streams = (MODE == kModeMfccPower) ? 2 : 1;
     for (; item < end; item += kExtractWarps) {
@@ -282,12 +353,17 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
             // ---- mel bands (lane = band, all frame pairs of the item) + log + store --------------------------
             {
                 const MelJob job{cur.f0, cur.T, cur.t0, cur.u, stream};
-                if constexpr (FAST) mel_fast<G, MODE>(lane, P, melp, prm, job);
+                if constexpr (FAST) mel_fast<G, MODE>(lane, P, taddr, prm, job);
                 else mel_rounds<G, MODE>(lane, P, melp, n_mels, prm, job);
             }
             __syncwarp();                                        // P reads done before the next pass 1 overwrites Y
             if (stream == n_streams - 1) cur = nxt;
         }
+    }
+    if constexpr (FAST) {
+        tmem::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem::dealloc(tmem_base, TmemMap<R>::kCols);
     }
 }
 
@@ -396,7 +472,7 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------------
-constexpr size_t kMaxSmem = 232448;      // 227 KB opt-in limit per CTA
+constexpr size_t kMaxSmem = 232448 - 64;  // 227 KB opt-in limit per CTA minus the static shared memory (TMEM base slot)
 
 // tuning knob (bench experiments only): SEPT_EXTRACT_WARPS lowers the warp count (occupancy-scaling measurements)
 static int warp_cap(int r_max) {

@@ -36,21 +36,27 @@ struct Geo {
     static constexpr int PPW = 32 / R;                           // packed frame pairs per warp
     static constexpr int FPW = 2 * PPW;                           // frames per item
     static constexpr int RS = 2 * R + 2;                          // pk2 per k2 row: [re: R][im: R][pad 2]; RS/2 odd spreads rows over banks
-    static constexpr int YP = 25 * RS + 4;                        // pk2 per pair
+    static constexpr int YROWS = R <= 16 ? 26 : 25;               // fused pass: row 25 is a second copy of row 0 (see pass2_split)
+    static constexpr int YP = YROWS * RS + 4;                     // pk2 per pair
     static constexpr int Y_PK2 = PPW * YP;                        // pk2 per warp
     static constexpr int Y_PK4 = Y_PK2 / 2;                       // the same in 16-byte units
-    static constexpr int PP = (NC + NC / 16 + 12) & ~1;           // pk2 per pair of the power tile (bins 0..NC+3, see bin_pos)
     static constexpr int TWS = R + 1;                             // f2 per split-twiddle row (odd: rows spread over banks)
     static constexpr int PS_ROUNDS = (PPW + 1) / 2;               // fused pass-2 + split: lane = (pair p % 2, row pair j < 13)
     static constexpr int P2_TASKS = PPW * 25;                     // pass-2 row tasks per item
     static constexpr int LEAD = 2;                                // floats in front of the staged span (halo + 8-byte alignment)
-    static_assert(PPW * PP <= Y_PK2, "power tile must fit in the Y tile it overwrites");
     static SEPT_HD int span(int hop) { return (FPW - 1) * hop + NFFT; }
-    // pk2 slot of bin k in a pair's power tile: natural order with one 8-byte gap after every 16 bins.  Bins with
-    // equal k mod 16 (the same k1 of different rows j, which the lanes of the fused pass store together) then fall
-    // into different banks, and quads of 4 bins starting at a multiple of 4 stay contiguous for the mel loads
-    // (layout chosen with tools/bank_sim.py: stores conflict free, mel gathers at 1.1x the minimum).
-    static SEPT_HD int bin_pos(int k) { return k + (k >> 4); }
+    // pk2 slot of bin k in a pair's power tile: natural order with gaps between blocks of bins, chosen per R so that
+    // the 8-byte stores of the split (lanes = rows j of one k1 in the fused pass: bins 16 t + k1 of 13 different blocks
+    // t; lanes = k1 in the R = 32 pass) spread over the 16 bank pairs.  Exhaustive search over k + ((c (k >> s)) >> d)
+    // against the kernel's store pattern: 76 / 80 wavefronts per item for R = 16 / 8 (64 is conflict free, the old
+    // k + k/16 cost 128), and the plain order is conflict free for R = 32.  The mel gathers adapt through the table
+    // scheduler (tables.h), so the layout is free to serve the stores.
+    static constexpr SEPT_HD int bin_pos(int k) {
+        return R == 32 ? k : R == 16 ? k + ((9 * (k >> 4)) >> 1) : k + ((9 * (k >> 3)) >> 2);
+    }
+    static constexpr int ZSLOT = bin_pos(NC) + 1, ZSLOTS = 3;     // kept at zero: idle slots of the mel program read them
+    static constexpr int PP = (ZSLOT + ZSLOTS + 1) & ~1;          // pk2 per pair of the power tile (bins 0..NC, zero slots)
+    static_assert(PPW * PP <= Y_PK2, "power tile must fit in the Y tile it overwrites");
     // fused pass 2 + split task of a lane in round r: pair p = 2r + lane/16, row pair j = lane%16 (idle when j >= 13)
     static SEPT_HD bool ps_task(int lane, int r, int& p, int& j) {
         p = 2 * r + (lane >> 4);
@@ -139,6 +145,9 @@ SEPT_HD void pass1(int lane, const float* stage, int hop, const f2* win2, pk2* Y
     pk2* y = Y + p * G::YP + n1;
 #pragma unroll
     for (int k2 = 0; k2 < 25; ++k2) { y[k2 * G::RS] = re[k2]; y[k2 * G::RS + R] = im[k2]; }
+    // the fused pass reads row 0 as its own partner; a second copy in row 25 keeps that 16-byte read out of the bank
+    // group of row 24 (rows 0 and 24 are 24 * RS * 8 bytes = a multiple of 128 apart)
+    if (G::YROWS == 26) { y[25 * G::RS] = re[0]; y[25 * G::RS + R] = im[0]; }
 }
 
 // load one k2 row (R complex samples of a frame pair) with 16-byte loads of two neighbouring real / imaginary parts
@@ -201,7 +210,7 @@ SEPT_HD bool split_load(int lane, int k2, const pk2* Y, const f2* tws, pk2& pk_,
 template <class G>
 SEPT_HD void pass2_split(int p, int j, const pk2* Y, const f2* tws, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
     constexpr int R = G::R;
-    const int rb = (25 - j) % 25;
+    const int rb = 25 - j;                                        // j = 0: row 25, the copy of row 0
     pk2 ur[R], ui[R], vr[R], vi[R];
     load_row<R>(Y + p * G::YP + j * G::RS, ur, ui);
     load_row<R>(Y + p * G::YP + rb * G::RS, vr, vi);
@@ -235,7 +244,11 @@ SEPT_HD void pass2_split_store(int p, int j, pk2* P, const pk2 (&pu)[G::R], cons
             base[G::bin_pos(kk)] = pv[k1];
         }
     }
-    if (j == 0) base[G::bin_pos(NC)] = pv[0];
+    if (j == 0) {
+        base[G::bin_pos(NC)] = pv[0];
+#pragma unroll
+        for (int z = 0; z < G::ZSLOTS; ++z) base[G::ZSLOT + z] = splat(0.f);
+    }
 }
 
 // after EVERY lane holds its 13 conjugate pairs in registers (warp barrier), the Y tile is overwritten by the power
@@ -251,6 +264,10 @@ SEPT_HD void split_store_all(int lane, pk2* P, const pk2 (&a)[13], const pk2 (&b
         if (k2 > 0 || on0) {
             base[G::bin_pos(k)] = a[k2];
             if (k != G::NC - k) base[G::bin_pos(G::NC - k)] = b[k2];   // k = 0 pairs with the Nyquist bin NC; NC/2 is its own partner
+            if (k == 0) {
+#pragma unroll
+                for (int z = 0; z < G::ZSLOTS; ++z) base[G::ZSLOT + z] = splat(0.f);
+            }
         }
         k += Pfa<R>::cK2;
         if (k >= G::NC) k -= G::NC;

@@ -58,11 +58,18 @@ inline std::vector<float> make_mel_fbank(int n_freqs, int n_mels, int sample_rat
 // weight, byte offset of the bin inside a frame pair's power tile}; rows of `width` entries per step.  Interval 0
 // (only its rising side is used, by band 0) is a short broadcast list in front (`head`).
 // The order in which a lane visits its bins is scheduled so that the 16 lanes of a half warp hit 16 different
-// 8-byte bank pairs in (nearly) every step; slots without a bin carry zero weights and the address of a bin another
-// lane of the half warp reads in that step (a broadcast costs nothing).  Weights carry the 1/4 of the kernel's 4|X|^2.
-// pk2 slot of bin k in a frame pair's power tile (the same function as Geo<R>::bin_pos in extract_core.cuh; hostsim
-// checks that they agree)
-inline int power_tile_pos(int k) { return k + (k >> 4); }
+// 8-byte bank pairs in (nearly) every step; slots without a bin read the tile's zero slot (one broadcast word).  Weights
+// carry the 1/4 of the kernel's 4|X|^2, so rising + falling = 1/4 for every bin.
+// pk2 slot of bin k in a frame pair's power tile (the same function as Geo<R>::bin_pos in extract_core.cuh, R = n_fft / 50;
+// hostsim checks that they agree)
+inline int power_tile_pos(int n_fft, int k) {
+    return n_fft == 1600 ? k : n_fft == 800 ? k + ((9 * (k >> 4)) >> 1) : k + ((9 * (k >> 3)) >> 2);
+}
+
+// first of the kZeroSlots consecutive slots of every pair's power tile that the split phase keeps at zero: what idle
+// program slots read (three bank pairs to choose from, so that the broadcast word rarely collides with a real read)
+constexpr int kZeroSlots = 3;
+inline int power_tile_zero_slot(int n_fft) { return power_tile_pos(n_fft, n_fft / 2) + 1; }
 
 struct MelStep { float up, dn; int32_t off, pad; };   // pad: step count of the round in the entries of its first step
 
@@ -72,8 +79,9 @@ struct MelProgram {
     int n_head = 0, width = 32, total_steps = 0;
 };
 
-template <class PosFn>
-inline void make_mel_program(int n_fft, int n_mels, int sample_rate, PosFn pos, MelProgram& prog) {
+inline void make_mel_program(int n_fft, int n_mels, int sample_rate, MelProgram& prog) {
+    auto pos = [n_fft](int k) { return power_tile_pos(n_fft, k); };
+    const int zslot = power_tile_zero_slot(n_fft);
     const int n_freqs = n_fft / 2 + 1;
     const double f_max = (double)(sample_rate / 2);
     std::vector<float> fb = make_mel_fbank(n_freqs, n_mels, sample_rate, 0.0, f_max);
@@ -117,38 +125,51 @@ inline void make_mel_program(int n_fft, int n_mels, int sample_rate, PosFn pos, 
             for (int h = 0; h < W; h += 16) {
                 const int h_end = h + 16 < W ? h + 16 : W;
                 int used[16] = {0};
+                bool may_idle = false;                               // some lane of this half warp may idle: keep one zero slot's bank pair free
+                for (int l = h; l < h_end; ++l) if ((int)rem[l].size() < left) may_idle = true;
                 // lanes with the least slack choose first
                 std::vector<int> order;
                 for (int l = h; l < h_end; ++l) order.push_back(l);
                 std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
                     return left - (int)rem[a].size() < left - (int)rem[b].size();
                 });
+                auto free_zero_banks = [&]() { int n = 0; for (int z = 0; z < kZeroSlots; ++z) n += used[(zslot + z) & 15] == 0; return n; };
+                auto load = [&](int k) {
+                    const int b = pos(k) & 15;
+                    const bool last_zero = may_idle && used[b] == 0 && ((b - zslot) & 15) < kZeroSlots && free_zero_banks() == 1;
+                    return used[b] + (last_zero ? 1 : 0);
+                };
                 for (int l : order) {
                     if (rem[l].empty()) continue;
                     const int slack = left - (int)rem[l].size();
                     int best = -1;
                     for (size_t c = 0; c < rem[l].size(); ++c)
-                        if (!used[pos(rem[l][c]) & 15]) { best = (int)c; break; }
+                        if (load(rem[l][c]) == 0) { best = (int)c; break; }
+                    if (best < 0 && slack > 0) continue;             // wait for a free bank pair
                     if (best < 0) {
-                        if (slack > 0) continue;                     // wait for a free bank pair
                         best = 0;
                         for (size_t c = 1; c < rem[l].size(); ++c)
-                            if (used[pos(rem[l][c]) & 15] < used[pos(rem[l][best]) & 15]) best = (int)c;
+                            if (load(rem[l][c]) < load(rem[l][best])) best = (int)c;
                     }
                     pick[l] = rem[l][best];
                     ++used[pos(pick[l]) & 15];
                     rem[l].erase(rem[l].begin() + best);
                 }
+                int z_best = 0;                                      // idle lanes of the half warp share the emptiest zero slot
+                for (int z = 1; z < kZeroSlots; ++z)
+                    if (used[(zslot + z) & 15] < used[(zslot + z_best) & 15]) z_best = z;
+                for (int l = h; l < h_end; ++l) if (pick[l] < 0) pick[l] = -2 - z_best;
             }
             for (int l = 0; l < W; ++l) {
+                const int i = 1 + r0 + l;
                 if (pick[l] >= 0) {
-                    const int k = pick[l], i = 1 + r0 + l;
-                    prog.entries.push_back(MelStep{up_w(k, i), dn_w(k, i), 8 * pos(k), 0});
+                    const int k = pick[l];
+                    // the last interval has no band above it: its rising weight is never used, store the complement of
+                    // the falling one so that "falling = 1/4 - rising" holds for every entry (unrolled path, extract.cu)
+                    const float dn = dn_w(k, i), up = i < n_mels ? up_w(k, i) : 0.25f - dn;
+                    prog.entries.push_back(MelStep{up, dn, 8 * pos(k), 0});
                 } else {
-                    int k = 0;                                       // idle slot: ride on a neighbour's read
-                    const int h = l & ~15;
-                    for (int o = h; o < h + 16 && o < W; ++o) if (pick[o] >= 0) { k = pick[o]; break; }
-                    prog.entries.push_back(MelStep{0.f, 0.f, 8 * pos(k), 0});
+                    prog.entries.push_back(MelStep{0.25f, 0.f, 8 * (zslot + (-2 - pick[l])), 0});   // idle: 1/4 x a zero slot
                 }
             }
         }

@@ -19,9 +19,10 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
     const int T = 1 + n / hop;
     std::vector<float> win = make_hann_periodic(n_fft), tws = make_split_twiddles(n_fft);
     MelProgram prog;
-    make_mel_program(n_fft, n_mels, 16000, power_tile_pos, prog);
+    make_mel_program(n_fft, n_mels, 16000, prog);
     for (int k = 0; k <= G::NC; ++k)
-        if (power_tile_pos(k) != G::bin_pos(k)) return 4;
+        if (power_tile_pos(n_fft, k) != G::bin_pos(k)) return 4;
+    if (power_tile_zero_slot(n_fft) != G::ZSLOT || kZeroSlots != G::ZSLOTS) return 4;
     static_assert(sizeof(MelStep) == sizeof(mel_step), "table entry layout");
     const mel_step* mprog = reinterpret_cast<const mel_step*>(prog.entries.data());
     std::vector<float> stage(G::stage_floats(hop), 0.f);
