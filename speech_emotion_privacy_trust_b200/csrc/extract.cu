@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 #include "extract.h"
 #include "extract_core.cuh"
@@ -123,8 +124,27 @@ __device__ __forceinline__ void mel_rounds(int lane, const pk2* P, const mel_ste
 template <int R> struct TmemMap {
     using F = FastMel<R>;
     static constexpr int kMelEntries = F::head + F::s0 + F::s1 + F::s2 + F::s3;
-    static constexpr int kMel = 0, kEnd = 2 * kMelEntries;
+    static constexpr int kTwEntries = R <= 16 ? R : 16;          // fused pass: W^k of the lane's row j for k1 < R; R = 32: rows k2 <= 12 of column k1
+    static constexpr int kMel = 0, kTw = 2 * kMelEntries, kWin = kTw + 2 * kTwEntries, kEnd = kWin + 50;
     static constexpr uint32_t kCols = kEnd <= 32 ? 32 : kEnd <= 64 ? 64 : kEnd <= 128 ? 128 : 256;
+};
+
+// the lane's 25 window pairs (w[2n], w[2n+1]) in n2 order, in registers for the whole of pass 1
+struct WinRegs {
+    uint32_t w[50];
+    __device__ __forceinline__ void load(uint32_t addr) { tmem::ld<50>(addr, w); tmem::wait_ld(); }
+    __device__ __forceinline__ f2 at(int /*idx*/, int n2) const { return f2{__uint_as_float(w[2 * n2]), __uint_as_float(w[2 * n2 + 1])}; }
+};
+
+// the lane's split twiddles, fetched four at a time while the split walks over them (k is a compile-time constant at
+// every call site, so the fetches sit at fixed places in the unrolled code; every lane of the warp must call)
+struct TwTmem {
+    uint32_t addr;
+    uint32_t buf[8];
+    __device__ __forceinline__ f2 at(int k) {
+        if (k % 4 == 0) { tmem::ld<8>(addr + 2 * k, buf); tmem::wait_ld(); }
+        return f2{__uint_as_float(buf[2 * (k % 4)]), __uint_as_float(buf[2 * (k % 4) + 1])};
+    }
 };
 
 // one round of N steps whose entries sit in registers mp[2 s] = rising weight, mp[2 s + 1] = byte offset
@@ -159,6 +179,35 @@ __device__ __forceinline__ void tmem_fill_mel(uint32_t taddr, int lane, const me
         v[2 * s + 1] = (uint32_t)st.off;
     }
     tmem::st<2 * M::kMelEntries>(taddr + M::kMel, v);
+}
+
+// ... and with its window samples (n2 order of pass 1) and split twiddles
+template <class G>
+__device__ __forceinline__ void tmem_fill_fft(uint32_t taddr, int lane, const f2* win2, const f2* tws) {
+    using M = TmemMap<G::R>;
+    constexpr int R = G::R;
+    {
+        uint32_t v[50];
+#pragma unroll
+        for (int n2 = 0; n2 < 25; ++n2) {
+            const f2 w = win2[Pfa<R>::in_index(lane % R, n2)];
+            v[2 * n2] = __float_as_uint(w.x);
+            v[2 * n2 + 1] = __float_as_uint(w.y);
+        }
+        tmem::st<50>(taddr + M::kWin, v);
+    }
+    {
+        uint32_t v[2 * M::kTwEntries];
+#pragma unroll
+        for (int k = 0; k < M::kTwEntries; ++k) {
+            f2 w{0.f, 0.f};
+            if (R <= 16) { const int j = (lane & 15) < 13 ? (lane & 15) : 12; w = tws[j * G::TWS + k]; }
+            else if (k <= 12) w = tws[k * G::TWS + lane];
+            v[2 * k] = __float_as_uint(w.x);
+            v[2 * k + 1] = __float_as_uint(w.y);
+        }
+        tmem::st<2 * M::kTwEntries>(taddr + M::kTw, v);
+    }
 }
 
 // mel bands, log, store of one item: no loops, no table reads from shared memory, one 64-bit address per item with
@@ -246,6 +295,7 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
         tmem::fence_after_sync();
         taddr = tmem::quarter_addr(tmem_base, warp, 0);
         tmem_fill_mel<G>(taddr, lane, melp);
+        tmem_fill_fft<G>(taddr, lane, win2, tws);
         tmem::wait_st();
         tmem::fence_before_sync();
     }
@@ -299,15 +349,24 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 #pragma unroll 1
         for (int stream = 0; stream < n_streams; ++stream) {
             const int deriv = (MODE == kModeMfccPower) ? stream : prm.deriv;
+            auto run_pass1 = [&](auto diff) {
+                if constexpr (FAST) {
+                    WinRegs win;
+                    win.load(taddr + TmemMap<R>::kWin);
+                    pass1<G, decltype(diff)::value>(lane, stage, hop, win, Y);
+                } else {
+                    pass1<G, decltype(diff)::value>(lane, stage, hop, WinShared{win2}, Y);
+                }
+            };
             if (cur.interior) {
                 if (stream == 0) { cp_async_wait_all(); __syncwarp(); }
-                if (deriv) pass1<G, true>(lane, stage, hop, win2, Y);
-                else pass1<G, false>(lane, stage, hop, win2, Y);
+                if (deriv) run_pass1(std::true_type{});
+                else run_pass1(std::false_type{});
             } else {
                 __syncwarp();
                 stage_item<G>(lane, cur.wav, cur.n, cur.t0, hop, deriv, stage);
                 __syncwarp();
-                pass1<G, false>(lane, stage, hop, win2, Y);
+                run_pass1(std::false_type{});
             }
             __syncwarp();                                        // stage is free, Y is complete
 
@@ -325,7 +384,16 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 #pragma unroll
                 for (int r = 0; r < ROUNDS; ++r) {
                     int p, j;
-                    if (G::ps_task(lane, r, p, j)) pass2_split<G>(p, j, Y, tws, pu[r], pv[r]);
+                    if constexpr (FAST) {
+                        // every lane runs the task (the twiddle fetch from tensor memory is warp-wide); lanes without one
+                        // repeat row pair 12 of their frame pair (same addresses: broadcasts) and store nothing
+                        G::ps_task(lane, r, p, j);
+                        TwTmem tw{taddr + TmemMap<R>::kTw};
+                        pass2_split<G>(p, j < 13 ? j : 12, Y, tw, pu[r], pv[r]);
+                    } else if (G::ps_task(lane, r, p, j)) {
+                        TwShared tw{tws + j * G::TWS};
+                        pass2_split<G>(p, j, Y, tw, pu[r], pv[r]);
+                    }
                 }
                 __syncwarp();
 #pragma unroll
@@ -340,9 +408,13 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                 // real split + power: every Z of the item goes to registers, then the tile is overwritten by P
                 pk2 a[13], b[13];
                 bool on0 = false;
+                TwTmem twt{taddr + TmemMap<R>::kTw};
+                TwStrided tws_col{tws + lane % R, G::TWS};
 #pragma unroll
                 for (int k2 = 0; k2 <= 12; ++k2) {
-                    const bool on = split_load<G>(lane, k2, Y, tws, a[k2], b[k2]);
+                    bool on;
+                    if constexpr (FAST) on = split_load<G>(lane, k2, Y, twt, a[k2], b[k2]);
+                    else on = split_load<G>(lane, k2, Y, tws_col, a[k2], b[k2]);
                     if (k2 == 0) on0 = on;
                 }
                 __syncwarp();

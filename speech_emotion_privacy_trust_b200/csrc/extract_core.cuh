@@ -113,13 +113,30 @@ SEPT_HD bool item_is_interior(int n, int t0, int hop) {
     return first >= 1 && first + G::span(hop) + 2 <= (long long)n - 1;
 }
 
+// ---- sources of the lane-constant tables.  The phase functions read the window and the split twiddles through one of
+// these: from shared memory (generic kernel, host emulation) or from registers filled out of tensor memory (extract.cu) --
+struct WinShared {                                               // win2[n] = (w[2n], w[2n+1])
+    const f2* win2;
+    SEPT_HD f2 at(int idx, int /*n2*/) const { return win2[idx]; }
+};
+struct TwShared {                                                // row of the lane: tws[j * TWS + k1]
+    const f2* row;
+    SEPT_HD f2 at(int k1) { return row[k1]; }
+};
+
+struct TwStrided {                                               // unfused pass (R = 32): the lane's twiddle of row k2
+    const f2* col;                                               // tws + k1
+    int stride;
+    SEPT_HD f2 at(int k2) { return col[k2 * stride]; }
+};
+
 // ---- pass 1: lane (p, n1) windows the 25 complex samples z[n] = xw[2n] + i xw[2n+1], n = (25 n1 + R n2) mod NC,
 // of frames 2p and 2p+1 and transforms them over n2 ------------------------------------------------------------
 // DIFF: the stage holds the raw waveform of an interior item and the stream wanted is np.gradient of it
 // (audio_feature_extraction.py:20): the central difference (x[j+1] - x[j-1]) / 2 is taken on the fly from the
 // neighbouring sample pairs, the 1/2 riding on the window (exact: a power of two).
-template <class G, bool DIFF>
-SEPT_HD void pass1(int lane, const float* stage, int hop, const f2* win2, pk2* Y) {
+template <class G, bool DIFF, class Win>
+SEPT_HD void pass1(int lane, const float* stage, int hop, const Win& win, pk2* Y) {
     constexpr int R = G::R;
     const int p = lane / R, n1 = lane % R;
     const f2* xa = reinterpret_cast<const f2*>(stage + G::LEAD + (2 * p) * hop);
@@ -128,7 +145,7 @@ SEPT_HD void pass1(int lane, const float* stage, int hop, const f2* win2, pk2* Y
 #pragma unroll
     for (int n2 = 0; n2 < 25; ++n2) {
         const int idx = Pfa<R>::in_index(n1, n2);
-        const f2 w = win2[idx];
+        const f2 w = win.at(idx, n2);
         if (!DIFF) {
             const f2 a = xa[idx], b = xb[idx];
             re[n2] = pk(a.x * w.x, b.x * w.x);
@@ -189,16 +206,16 @@ SEPT_HD void split_pair(pk4 zk, pk4 zm, pk2 twr, pk2 twi, pk2& pk_, pk2& pm_) {
 
 // iteration k2 (0..12) of the split: lane (p, k1) pairs Z at (k1, k2) with Z at (R-k1, 25-k2).
 // Returns false when the lane has nothing to do (row 0 is its own partner: only k1 <= R/2 work).
-template <class G>
-SEPT_HD bool split_load(int lane, int k2, const pk2* Y, const f2* tws, pk2& pk_, pk2& pm_) {
+template <class G, class Tw>
+SEPT_HD bool split_load(int lane, int k2, const pk2* Y, Tw& tws, pk2& pk_, pk2& pm_) {
     constexpr int R = G::R;
     const int p = lane / R, k1 = lane % R, km = (R - k1) % R;
+    const f2 tw = tws.at(k2);                                     // the lane's twiddle of row k2; fetched by every lane (warp-wide source)
     if (k2 == 0 && k1 > R / 2) return false;
     const int rb = (25 - k2) % 25;
     const pk2* yk = Y + p * G::YP + k2 * G::RS + k1;
     const pk2* ym = Y + p * G::YP + rb * G::RS + km;
     const pk4 zk{yk[0], yk[R]}, zm{ym[0], ym[R]};
-    const f2 tw = tws[k2 * G::TWS + k1];
     split_pair(zk, zm, splat(tw.x), splat(tw.y), pk_, pm_);
     return true;
 }
@@ -207,8 +224,8 @@ SEPT_HD bool split_load(int lane, int k2, const pk2* Y, const f2* tws, pk2& pk_,
 // splits them against each other without another trip through shared memory.  pu[k1] = 4|X|^2 at bin CRT(k1, j),
 // pv[k1] = 4|X|^2 at bin CRT(k1, 25-j).  Row 0 (j = 0) is its own partner: pu holds the whole row and pv[0] the
 // Nyquist bin. ------------------------------------------------------------------------------------------------------
-template <class G>
-SEPT_HD void pass2_split(int p, int j, const pk2* Y, const f2* tws, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
+template <class G, class Tw>
+SEPT_HD void pass2_split(int p, int j, const pk2* Y, Tw& tw, pk2 (&pu)[G::R], pk2 (&pv)[G::R]) {
     constexpr int R = G::R;
     const int rb = 25 - j;                                        // j = 0: row 25, the copy of row 0
     pk2 ur[R], ui[R], vr[R], vi[R];
@@ -216,12 +233,10 @@ SEPT_HD void pass2_split(int p, int j, const pk2* Y, const f2* tws, pk2 (&pu)[G:
     load_row<R>(Y + p * G::YP + rb * G::RS, vr, vi);
     Dft<R>::run(ur, ui);
     Dft<R>::run(vr, vi);
-    const f2* tw = tws + j * G::TWS;
 #pragma unroll
     for (int k1 = 0; k1 < R; ++k1) {
-        constexpr int dummy = 0; (void)dummy;
         const int km = (R - k1) % R;
-        const f2 w = tw[k1];
+        const f2 w = tw.at(k1);
         split_pair(pk4{ur[k1], ui[k1]}, pk4{vr[km], vi[km]}, splat(w.x), splat(w.y), pu[k1], pv[km]);
     }
 }

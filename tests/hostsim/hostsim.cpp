@@ -38,8 +38,8 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
         for (int lane = 0; lane < 32; ++lane)
             stage_item<G>(lane, wav.data(), n, t0, hop, interior ? 0 : deriv, stage.data());
         for (int lane = 0; lane < 32; ++lane) {
-            if (interior && deriv) pass1<G, true>(lane, stage.data(), hop, win2, Yp);
-            else pass1<G, false>(lane, stage.data(), hop, win2, Yp);
+            if (interior && deriv) pass1<G, true>(lane, stage.data(), hop, WinShared{win2}, Yp);
+            else pass1<G, false>(lane, stage.data(), hop, WinShared{win2}, Yp);
         }
         const f2* tw2 = reinterpret_cast<const f2*>(tws.data());
         if constexpr (R <= 16) {
@@ -47,7 +47,10 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
             int p, j;
             for (int r = 0; r < G::PS_ROUNDS; ++r)
                 for (int lane = 0; lane < 32; ++lane)
-                    if (G::ps_task(lane, r, p, j)) pass2_split<G>(p, j, Yp, tw2, pu[r][lane], pv[r][lane]);
+                    if (G::ps_task(lane, r, p, j)) {
+                        TwShared tw{tw2 + j * G::TWS};
+                        pass2_split<G>(p, j, Yp, tw, pu[r][lane], pv[r][lane]);
+                    }
             for (int r = 0; r < G::PS_ROUNDS; ++r)
                 for (int lane = 0; lane < 32; ++lane)
                     if (G::ps_task(lane, r, p, j)) pass2_split_store<G>(p, j, P, pu[r][lane], pv[r][lane]);
@@ -57,7 +60,8 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
             bool on0[32];
             for (int lane = 0; lane < 32; ++lane)
                 for (int k2 = 0; k2 <= 12; ++k2) {
-                    const bool on = split_load<G>(lane, k2, Yp, tw2, a[lane][k2], b[lane][k2]);
+                    TwStrided tw{tw2 + lane % R, G::TWS};
+                    const bool on = split_load<G>(lane, k2, Yp, tw, a[lane][k2], b[lane][k2]);
                     if (k2 == 0) on0[lane] = on;
                 }
             for (int lane = 0; lane < 32; ++lane) split_store_all<G>(lane, P, a[lane], b[lane], on0[lane]);
