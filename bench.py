@@ -231,6 +231,8 @@ def run_b200(args):
     _lib.check(_lib.lib().sept_init(N_MELS))
 
     lengths = corpus_lengths(args.utts, 1234 + rank)
+    if args.round_lengths > 1:                                    # debug only: every utterance starts on an aligned sample
+        lengths = (lengths // args.round_lengths) * args.round_lengths
     utt_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
     wav = synth_corpus_device(lengths, 4321 + rank, dev)
     batch = extraction.RaggedAudio(wav, utt_off)
@@ -439,6 +441,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary metric, e2e and cpu_baseline (profiling runs)")
     ap.add_argument("--n-fft", type=int, default=N_FFT, help="debug only: time another FFT size (the metric is quoted on 800)")
+    ap.add_argument("--round-lengths", type=int, default=1, help="debug only: round utterance lengths down to a multiple (alignment experiments)")
     ap.add_argument("--utts", type=int, default=CORPUS_UTTS, help="utterances per GPU (debug only; the metric is quoted on the default)")
     args = ap.parse_args()
     if args.impl == "reference":
