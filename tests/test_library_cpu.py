@@ -107,6 +107,39 @@ def test_kernel_phase_functions_on_host_gradient_stream(hostsim, golden_extracti
     assert np.max(np.abs(got - ref)) < 1e-3
 
 
+@pytest.fixture(scope="module")
+def melprog(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("melprog") / "mel_program"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", str(CSRC), str(REPO / "tests" / "hostsim" / "mel_program.cpp"), "-o", str(exe)],
+                   check=True)
+    return exe
+
+
+@pytest.mark.parametrize("n_fft", [400, 800, 1600])
+@pytest.mark.parametrize("n_mels", [1, 2, 5, 31, 32, 33, 40, 64, 100, 128, 200, 256, 512])
+def test_mel_gather_program_encodes_the_filterbank(melprog, n_fft, n_mels):
+    """The per-lane mel gather program (csrc/tables.h) holds every non-zero weight of melscale_fbanks exactly once, idle
+    slots read a zero slot, and falling = 1/4 - rising for every entry (what the unrolled kernel path relies on)."""
+    r = subprocess.run([str(melprog), str(n_fft), str(n_mels)], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, f"mel_program exit code {r.returncode}"
+    tag, steps, wavefronts, head = r.stdout.split()
+    assert tag == "ok"
+    if n_mels == 128:                                    # the reference's filterbank: the schedule stays near conflict free
+        assert int(wavefronts) <= 1.25 * 2 * int(steps)
+
+
+def test_fast_mel_step_counts_match_the_compiled_constants(melprog):
+    """FastMel<R> in extract_core.cuh (compile-time step counts of the unrolled 128-band path) vs the built program."""
+    import re
+    src = (CSRC / "extract_core.cuh").read_text()
+    for n_fft, R in ((400, 8), (800, 16), (1600, 32)):
+        m = re.search(rf"FastMel<{R}> \{{ static constexpr int head = (\d+), s0 = (\d+), s1 = (\d+), s2 = (\d+), s3 = (\d+);", src)
+        assert m, R
+        head, *s = map(int, m.groups())
+        out = subprocess.run([str(melprog), str(n_fft), "128"], stdout=subprocess.PIPE, text=True, check=True).stdout.split()
+        assert int(out[1]) == sum(s) and int(out[3]) == head
+
+
 def test_dropin_state_dict_keys_match_reference():
     import json
     from speech_emotion_privacy_trust_b200 import dropin
