@@ -148,6 +148,15 @@ int sept_cloak_grl_bwd_f32(const float* g_a_dev, const float* g_b_dev, float lam
 /* Backward of GradientReversalFunction (model/reversal_gradient.py:19-23): dx = -lambda * g. */
 int sept_grl_bwd_f32(const float* g_dev, float lambda, int64_t n, float* dx_dev, sept_stream_t stream);
 
+/* Class-balance noise augmentation (preprocess_data/preprocess_adversary_data.py:392-421): job j adds to row
+ * job_row[j] of data_dev (n_rows, row_elems) the noise samples draw_id[job_ptr[j] .. job_ptr[j+1]) in that order -- the
+ * reference writes the noisy copy through an alias of the source window, so a window drawn m times carries the sum of its
+ * m samples, shared by all its copies.  noise_dev NULL: sample t is N(0, std) from Philox(seed, t); else row t of
+ * noise_dev (n_draws, row_elems).  Rows of different jobs must be distinct.  At most 65535 jobs per call. */
+int sept_add_noise_rows_f32(float* data_dev, const int64_t* job_row_dev, const int32_t* job_ptr_dev,
+                            const int64_t* draw_id_dev, int n_jobs, int row_elems, uint64_t seed, float std,
+                            const float* noise_dev, sept_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/sept.h"
+#include "augment.h"
 #include "cloak.h"
 #include "extract.h"
 #include "norm.h"
@@ -377,6 +378,22 @@ int sept_grl_bwd_f32(const float* g, float lambda, int64_t n, float* dx, sept_st
     if (!g || !dx || n < 0) return fail(SEPT_E_BADARG, "sept_grl_bwd_f32: bad argument");
     if (!aligned16(g) || !aligned16(dx)) return fail(SEPT_E_BADARG, "sept_grl_bwd_f32: pointers must be 16-byte aligned");
     SEPT_CUDA(sept::launch_grl_bwd(g, lambda, (size_t)n, dx, static_cast<cudaStream_t>(stream)));
+    return SEPT_OK;
+}
+
+int sept_add_noise_rows_f32(float* data_dev, const int64_t* job_row_dev, const int32_t* job_ptr_dev, const int64_t* draw_id_dev,
+                            int n_jobs, int row_elems, uint64_t seed, float std, const float* noise_dev, sept_stream_t stream) {
+    if (n_jobs == 0) return SEPT_OK;
+    if (!data_dev || !job_row_dev || !job_ptr_dev || !draw_id_dev || n_jobs < 0 || row_elems <= 0)
+        return fail(SEPT_E_BADARG, "sept_add_noise_rows_f32: bad argument");
+    if (row_elems % 4 != 0) return fail(SEPT_E_UNSUPPORTED, "sept_add_noise_rows_f32: row_elems=%d must be a multiple of 4", row_elems);
+    if (n_jobs > 65535) return fail(SEPT_E_UNSUPPORTED, "sept_add_noise_rows_f32: n_jobs=%d exceeds 65535 per call", n_jobs);
+    if (!aligned16(data_dev) || (noise_dev && !aligned16(noise_dev)))
+        return fail(SEPT_E_BADARG, "sept_add_noise_rows_f32: pointers must be 16-byte aligned");
+    sept::AddNoiseParams p{};
+    p.data = data_dev; p.job_row = job_row_dev; p.job_ptr = job_ptr_dev; p.draw_id = draw_id_dev; p.n_jobs = n_jobs;
+    p.row_elems = row_elems; p.seed = seed; p.std = std; p.noise = noise_dev;
+    SEPT_CUDA(sept::launch_add_noise(p, static_cast<cudaStream_t>(stream)));
     return SEPT_OK;
 }
 
