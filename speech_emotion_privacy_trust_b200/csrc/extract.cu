@@ -441,21 +441,25 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 
 
 // ---- MFCC phase 2: dB with the per-utterance floor, then DCT (transforms/_transforms.py:714-717) ------------
-// One CTA handles kDctFrames consecutive global frames (they may straddle utterances).  The load phase converts the
-// two mel-power streams into the three clamped dB streams in shared memory (np.gradient(x, 2) == np.gradient(x) / 2
-// exactly, so stream 2 is the dB of a quarter of stream 1's power); then thread (f = tid % 32, q = tid / 32) produces
-// coefficients [10q, 10q+10) of the three streams of frame f: 30 accumulators, 3 + 3 shared loads per 30 FMAs.
-constexpr int kDctFrames = 32;
+// One CTA handles kDctFrames = 64 consecutive global frames (they may straddle utterances).  The load phase converts the
+// two mel-power streams to dB in shared memory (unclamped).  Thread (f = tid % 32, q = tid / 32) then produces
+// coefficients [10q, 10q+10) of the three streams for the frame PAIR (f, f + 32) packed in pk2: 30 packed accumulators,
+// and per mel band 4 scalar loads + 5 broadcast weight loads for 30 FFMA2 -- the weights are fetched once per two
+// frames, which takes the kernel from the shared-memory pipe's limit to the FMA pipe's.  The top_db floors are applied
+// on the fly; stream 2 (np.gradient(x, 2) == np.gradient(x) / 2 exactly, a quarter of stream 1's power) is stream 1's
+// dB minus 10 log10(4), with amplitude_to_DB's amin clamp (-100 dB) folded into its floor.
+constexpr int kDctFrames = 64;
 constexpr int kDctThreads = 128;
 constexpr int kDctNM = 128, kDctNC = 40, kDctDS = 40, kDctXS = kDctNM + 1;
-constexpr size_t kDctSmem = (kDctNM * kDctDS + 3 * kDctFrames * kDctXS + 4 * kDctFrames) * 4;
+constexpr size_t kDctSmem = (kDctNM * kDctDS + 2 * kDctFrames * kDctXS + 4 * kDctFrames) * 4;
+constexpr float kDbQuarter = 6.02059991327962390f;     // 10 log10(4)
 
 __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctParams prm) {
     constexpr int NM = kDctNM, NC = kDctNC, DS = kDctDS, XS = kDctXS;
     extern __shared__ __align__(16) unsigned char dct_smem[];
     float* D = reinterpret_cast<float*>(dct_smem);                                   // [NM][DS]
-    float* X = D + NM * DS;                                                          // [3][kDctFrames][XS] clamped dB
-    int* frame_utt = reinterpret_cast<int*>(X + 3 * kDctFrames * XS);                // [kDctFrames]
+    float* X = D + NM * DS;                                                          // [2][kDctFrames][XS] dB, unclamped
+    int* frame_utt = reinterpret_cast<int*>(X + 2 * kDctFrames * XS);                // [kDctFrames]
     float* frame_floor = reinterpret_cast<float*>(frame_utt + kDctFrames);           // [3][kDctFrames]
     const long long g0 = (long long)blockIdx.x * kDctFrames;
     for (int i = threadIdx.x; i < NM * NC / 4; i += kDctThreads)
@@ -467,58 +471,57 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
         const float max0 = __int_as_float(prm.utt_max[lo_]), max1 = __int_as_float(prm.utt_max[prm.n_utts + lo_]);
         frame_floor[threadIdx.x] = power_to_db(max0) - prm.top_db;
         frame_floor[kDctFrames + threadIdx.x] = power_to_db(max1) - prm.top_db;
-        frame_floor[2 * kDctFrames + threadIdx.x] = power_to_db(0.25f * max1) - prm.top_db;
+        // power_to_db(p / 4) = max(power_to_db(p) - 10 log10 4, -100): the amin clamp rides on the floor
+        frame_floor[2 * kDctFrames + threadIdx.x] = fmaxf(power_to_db(0.25f * max1) - prm.top_db, -100.0f);
     }
-    // load phase: all 16 float4 loads of a thread are issued before the first is used; a warp covers 4 frames x 8
-    // quads per step (128-byte segments in HBM, and 32 distinct banks for its scalar stores into the 129-float rows)
+    // load phase: 16 float4 loads of a thread are issued before the first is used; a warp covers 4 frames x 8 quads per
+    // step (128-byte segments in HBM, and 32 distinct banks for its scalar stores into the 129-float rows)
     {
-        constexpr int NIT = 2 * kDctFrames * (NM / 4) / kDctThreads;                 // 16
+        constexpr int NIT = 16, PASSES = 2 * kDctFrames * (NM / 4) / kDctThreads / NIT;   // 2 passes of 16
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int f_lo = lane >> 3, m4_lo = lane & 7;
-        float4 pw[NIT];
+#pragma unroll 1
+        for (int pass = 0; pass < PASSES; ++pass) {
+            float4 pw[NIT];
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int combo = it * 4 + warp, s = combo >> 5, rem = combo & 31;
-            const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
-            const long long g = g0 + f;
-            pw[it] = g < prm.total_frames
-                         ? __ldg(reinterpret_cast<const float4*>(prm.power + ((long long)s * prm.total_frames + g) * NM) + m4)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();                                                             // frame_floor is ready
+            for (int it = 0; it < NIT; ++it) {
+                const int combo = (pass * NIT + it) * 4 + warp, s = combo >> 6, rem = combo & 63;
+                const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
+                const long long g = g0 + f;
+                pw[it] = g < prm.total_frames
+                             ? __ldg(reinterpret_cast<const float4*>(prm.power + ((long long)s * prm.total_frames + g) * NM) + m4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int combo = it * 4 + warp, s = combo >> 5, rem = combo & 31;
-            const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
-            const float v[4] = {pw[it].x, pw[it].y, pw[it].z, pw[it].w};
-            float* x = X + (s * kDctFrames + f) * XS + 4 * m4;
-            const float fl = frame_floor[s * kDctFrames + f];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) x[c] = fmaxf(power_to_db(v[c]), fl);
-            if (s == 1) {
-                float* x2 = X + (2 * kDctFrames + f) * XS + 4 * m4;
-                const float fl2 = frame_floor[2 * kDctFrames + f];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) x2[c] = fmaxf(power_to_db(0.25f * v[c]), fl2);
+            for (int it = 0; it < NIT; ++it) {
+                const int combo = (pass * NIT + it) * 4 + warp, s = combo >> 6, rem = combo & 63;
+                const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
+                float* x = X + (s * kDctFrames + f) * XS + 4 * m4;
+                x[0] = power_to_db(pw[it].x); x[1] = power_to_db(pw[it].y);
+                x[2] = power_to_db(pw[it].z); x[3] = power_to_db(pw[it].w);
             }
         }
     }
     __syncthreads();
     const int f = threadIdx.x & 31, q = threadIdx.x >> 5;
-    const long long g = g0 + f;
-    if (g >= prm.total_frames) return;
-    float acc[3][10];
+    pk2 acc[3][10];
 #pragma unroll
     for (int s = 0; s < 3; ++s)
 #pragma unroll
-        for (int c = 0; c < 10; ++c) acc[s][c] = 0.f;
-    const float* x0 = X + f * XS;
-    const float* x1 = x0 + kDctFrames * XS;
-    const float* x2 = x1 + kDctFrames * XS;
+        for (int c = 0; c < 10; ++c) acc[s][c] = splat(0.f);
+    const float* xa0 = X + f * XS;                                                   // frame f, stream 0
+    const float* xb0 = xa0 + 32 * XS;                                                // frame f + 32
+    const float* xa1 = xa0 + kDctFrames * XS;
+    const float* xb1 = xb0 + kDctFrames * XS;
+    const pk2 fl0 = pk(frame_floor[f], frame_floor[f + 32]);
+    const pk2 fl1 = pk(frame_floor[kDctFrames + f], frame_floor[kDctFrames + f + 32]);
+    const pk2 fl2 = pk(frame_floor[2 * kDctFrames + f], frame_floor[2 * kDctFrames + f + 32]);
     const float* drow = D + 10 * q;
+    auto max2 = [](pk2 a, pk2 b) { return pk(fmaxf(lo(a), lo(b)), fmaxf(hi(a), hi(b))); };
 #pragma unroll 4
     for (int m = 0; m < NM; ++m) {
-        const float d0 = x0[m], d1 = x1[m], d2 = x2[m];
+        const pk2 r0 = pk(xa0[m], xb0[m]), r1 = pk(xa1[m], xb1[m]);
+        const pk2 d0 = max2(r0, fl0), d1 = max2(r1, fl1), d2 = max2(r1 - splat(kDbQuarter), fl2);
         const float2 w01 = *reinterpret_cast<const float2*>(drow + m * DS);
         const float2 w23 = *reinterpret_cast<const float2*>(drow + m * DS + 2);
         const float2 w45 = *reinterpret_cast<const float2*>(drow + m * DS + 4);
@@ -527,20 +530,27 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
         const float w[10] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w89.x, w89.y};
 #pragma unroll
         for (int c = 0; c < 10; ++c) {
-            acc[0][c] = fmaf(d0, w[c], acc[0][c]);
-            acc[1][c] = fmaf(d1, w[c], acc[1][c]);
-            acc[2][c] = fmaf(d2, w[c], acc[2][c]);
+            const pk2 wc = splat(w[c]);
+            acc[0][c] = fma2(d0, wc, acc[0][c]);
+            acc[1][c] = fma2(d1, wc, acc[1][c]);
+            acc[2][c] = fma2(d2, wc, acc[2][c]);
         }
     }
-    const int u = frame_utt[f];
-    const long long f0 = prm.frame_off[u];
-    const int T = (int)(prm.frame_off[u + 1] - f0);
-    const int t = (int)(g - f0);
-    float* o = prm.out + f0 * (3 * NC) + t;
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+    for (int half = 0; half < 2; ++half) {
+        const int fr = f + 32 * half;
+        const long long g = g0 + fr;
+        if (g >= prm.total_frames) continue;
+        const int u = frame_utt[fr];
+        const long long f0 = prm.frame_off[u];
+        const int T = (int)(prm.frame_off[u + 1] - f0);
+        const int t = (int)(g - f0);
+        float* o = prm.out + f0 * (3 * NC) + t;
 #pragma unroll
-        for (int c = 0; c < 10; ++c) o[(long long)(s * NC + 10 * q + c) * T] = acc[s][c];
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int c = 0; c < 10; ++c) o[(long long)(s * NC + 10 * q + c) * T] = half ? hi(acc[s][c]) : lo(acc[s][c]);
+    }
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------------
