@@ -48,7 +48,7 @@ struct Geo {
     // pk2 slot of bin k in a pair's power tile: natural order with gaps between blocks of bins, chosen per R so that
     // the 8-byte stores of the split (lanes = rows j of one k1 in the fused pass: bins 16 t + k1 of 13 different blocks
     // t; lanes = k1 in the R = 32 pass) spread over the 16 bank pairs.  Exhaustive search over k + ((c (k >> s)) >> d)
-    // against the kernel's store pattern: 76 / 80 wavefronts per item for R = 16 / 8 (64 is conflict free, the old
+    // against the kernel's store pattern (tools/tile_layout_search.py): 76 / 80 wavefronts per item for R = 16 / 8 (64 is conflict free, the old
     // k + k/16 cost 128), and the plain order is conflict free for R = 32.  The mel gathers adapt through the table
     // scheduler (tables.h), so the layout is free to serve the stores.
     static constexpr SEPT_HD int bin_pos(int k) {
@@ -303,25 +303,6 @@ SEPT_HD void mel_round(const pk2* P, const mel_step* e, int n_steps, int width, 
 #pragma unroll 2
     for (int s = 0; s < n_steps; ++s) {
         const mel_step st = e[s * width];
-        const pk2 up = splat(st.up), dn = splat(st.dn);
-#pragma unroll
-        for (int p = 0; p < G::PPW; ++p) {
-            const pk2 v = *reinterpret_cast<const pk2*>(base + st.off + p * (G::PP * 8));
-            U[p] = fma2(v, up, U[p]);
-            D[p] = fma2(v, dn, D[p]);
-        }
-    }
-}
-
-// the same with a compile-time step count: fully unrolled, every load of the round can be in flight at once
-template <class G, int N>
-SEPT_HD void mel_round_fixed(const pk2* P, const mel_step* e, pk2 (&U)[G::PPW], pk2 (&D)[G::PPW]) {
-#pragma unroll
-    for (int p = 0; p < G::PPW; ++p) { U[p] = splat(0.f); D[p] = splat(0.f); }
-    const unsigned char* base = reinterpret_cast<const unsigned char*>(P);
-#pragma unroll
-    for (int s = 0; s < N; ++s) {
-        const mel_step st = e[s * 32];
         const pk2 up = splat(st.up), dn = splat(st.dn);
 #pragma unroll
         for (int p = 0; p < G::PPW; ++p) {

@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Shared-memory wavefront simulator for the extraction kernel's access patterns (design aid, CPU only).
+"""[Historical: models the tile layouts and lane->task maps of the kernel generations before the mel gather program;
+the current layout search is tools/tile_layout_search.py and the gather schedule is checked by tests/hostsim/mel_program.cpp.]
+Shared-memory wavefront simulator for the extraction kernel's access patterns (design aid, CPU only).
 Model: 32 banks x 4 B; a warp access of 8 B/lane is served as 2 half-warps, 16 B/lane as 4 quarter-warps; within a
 group the wavefront count is the max over banks of DISTINCT 4-byte words touched (same word = broadcast)."""
 import sys
