@@ -443,26 +443,29 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 // ---- MFCC phase 2: dB with the per-utterance floor, then DCT (transforms/_transforms.py:714-717) ------------
 // One CTA handles kDctFrames = 64 consecutive global frames (they may straddle utterances).  The load phase converts the
 // two mel-power streams to dB in shared memory (unclamped).  Thread (f = tid % 32, q = tid / 32) then produces
-// coefficients [10q, 10q+10) of the three streams for the frame PAIR (f, f + 32) packed in pk2: 30 packed accumulators,
-// and per mel band 4 scalar loads + 5 broadcast weight loads for 30 FFMA2 -- the weights are fetched once per two
-// frames, which takes the kernel from the shared-memory pipe's limit to the FMA pipe's.  The top_db floors are applied
-// on the fly; stream 2 (np.gradient(x, 2) == np.gradient(x) / 2 exactly, a quarter of stream 1's power) is stream 1's
-// dB minus 10 log10(4), with amplitude_to_DB's amin clamp (-100 dB) folded into its floor.
+// coefficients [10q, 10q+10) of the three streams for the frame PAIR (f, f + 32) packed in pk2 (30 packed accumulators;
+// the weights are fetched once per two frames).  The ortho DCT-II basis is symmetric, D[127-m][c] = (-1)^c D[m][c], so
+// bands m and 127-m are folded first: even coefficients take x[m] + x[127-m], odd ones the difference -- 15 + 15 FFMA2
+// per band pair instead of 60, and only half of the basis in shared memory.  The top_db floors are applied on the fly;
+// stream 2 (np.gradient(x, 2) == np.gradient(x) / 2 exactly, a quarter of stream 1's power) is stream 1's dB minus
+// 10 log10(4), with amplitude_to_DB's amin clamp (-100 dB) folded into its floor.  Rows of the dB tile are rotated by the
+// frame index instead of padded (conflict-free scalar reads, exactly 64 KB), which lets three CTAs share an SM.
 constexpr int kDctFrames = 64;
 constexpr int kDctThreads = 128;
-constexpr int kDctNM = 128, kDctNC = 40, kDctDS = 40, kDctXS = kDctNM + 1;
-constexpr size_t kDctSmem = (kDctNM * kDctDS + 2 * kDctFrames * kDctXS + 4 * kDctFrames) * 4;
+constexpr int kDctNM = 128, kDctNC = 40, kDctDS = 40, kDctHalf = kDctNM / 2;
+constexpr size_t kDctSmem = (kDctHalf * kDctDS + 2 * kDctFrames * kDctNM + 4 * kDctFrames) * 4;   // 75 KB
 constexpr float kDbQuarter = 6.02059991327962390f;     // 10 log10(4)
 
-__global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctParams prm) {
-    constexpr int NM = kDctNM, NC = kDctNC, DS = kDctDS, XS = kDctXS;
+__global__ void __launch_bounds__(kDctThreads, 3) mfcc_dct_kernel(const MfccDctParams prm) {
+    constexpr int NM = kDctNM, NC = kDctNC, DS = kDctDS;
     extern __shared__ __align__(16) unsigned char dct_smem[];
-    float* D = reinterpret_cast<float*>(dct_smem);                                   // [NM][DS]
-    float* X = D + NM * DS;                                                          // [2][kDctFrames][XS] dB, unclamped
-    int* frame_utt = reinterpret_cast<int*>(X + 2 * kDctFrames * XS);                // [kDctFrames]
+    float* D = reinterpret_cast<float*>(dct_smem);                                   // [NM / 2][DS]: basis rows 0..63
+    float* X = D + kDctHalf * DS;                                                    // [2][kDctFrames][NM] dB, unclamped; band m of
+                                                                                     // frame f at column (m + f) % NM
+    int* frame_utt = reinterpret_cast<int*>(X + 2 * kDctFrames * NM);                // [kDctFrames]
     float* frame_floor = reinterpret_cast<float*>(frame_utt + kDctFrames);           // [3][kDctFrames]
     const long long g0 = (long long)blockIdx.x * kDctFrames;
-    for (int i = threadIdx.x; i < NM * NC / 4; i += kDctThreads)
+    for (int i = threadIdx.x; i < kDctHalf * NC / 4; i += kDctThreads)
         reinterpret_cast<float4*>(D)[i] = reinterpret_cast<const float4*>(prm.dct)[i];
     if (threadIdx.x < kDctFrames) {
         const long long g = g0 + threadIdx.x;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
         frame_floor[2 * kDctFrames + threadIdx.x] = fmaxf(power_to_db(0.25f * max1) - prm.top_db, -100.0f);
     }
     // load phase: 16 float4 loads of a thread are issued before the first is used; a warp covers 4 frames x 8 quads per
-    // step (128-byte segments in HBM, and 32 distinct banks for its scalar stores into the 129-float rows)
+    // step (128-byte segments in HBM, and 32 distinct banks for its scalar stores into the rotated rows)
     {
         constexpr int NIT = 16, PASSES = 2 * kDctFrames * (NM / 4) / kDctThreads / NIT;   // 2 passes of 16
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -496,9 +499,10 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
             for (int it = 0; it < NIT; ++it) {
                 const int combo = (pass * NIT + it) * 4 + warp, s = combo >> 6, rem = combo & 63;
                 const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
-                float* x = X + (s * kDctFrames + f) * XS + 4 * m4;
-                x[0] = power_to_db(pw[it].x); x[1] = power_to_db(pw[it].y);
-                x[2] = power_to_db(pw[it].z); x[3] = power_to_db(pw[it].w);
+                float* x = X + (s * kDctFrames + f) * NM;
+                const int col = 4 * m4 + f;
+                x[col & (NM - 1)] = power_to_db(pw[it].x); x[(col + 1) & (NM - 1)] = power_to_db(pw[it].y);
+                x[(col + 2) & (NM - 1)] = power_to_db(pw[it].z); x[(col + 3) & (NM - 1)] = power_to_db(pw[it].w);
             }
         }
     }
@@ -509,19 +513,24 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
     for (int s = 0; s < 3; ++s)
 #pragma unroll
         for (int c = 0; c < 10; ++c) acc[s][c] = splat(0.f);
-    const float* xa0 = X + f * XS;                                                   // frame f, stream 0
-    const float* xb0 = xa0 + 32 * XS;                                                // frame f + 32
-    const float* xa1 = xa0 + kDctFrames * XS;
-    const float* xb1 = xb0 + kDctFrames * XS;
+    const float* xa0 = X + f * NM;                                                   // frame f, stream 0 (rotated by f)
+    const float* xb0 = xa0 + 32 * NM;                                                // frame f + 32 (rotated by f + 32)
+    const float* xa1 = xa0 + kDctFrames * NM;
+    const float* xb1 = xb0 + kDctFrames * NM;
     const pk2 fl0 = pk(frame_floor[f], frame_floor[f + 32]);
     const pk2 fl1 = pk(frame_floor[kDctFrames + f], frame_floor[kDctFrames + f + 32]);
     const pk2 fl2 = pk(frame_floor[2 * kDctFrames + f], frame_floor[2 * kDctFrames + f + 32]);
     const float* drow = D + 10 * q;
     auto max2 = [](pk2 a, pk2 b) { return pk(fmaxf(lo(a), lo(b)), fmaxf(hi(a), hi(b))); };
-#pragma unroll 4
-    for (int m = 0; m < NM; ++m) {
-        const pk2 r0 = pk(xa0[m], xb0[m]), r1 = pk(xa1[m], xb1[m]);
+#pragma unroll 2
+    for (int m = 0; m < kDctHalf; ++m) {
+        const int ca = (m + f) & (NM - 1), cb = (m + f + 32) & (NM - 1);             // band m of the two frames
+        const int ma = (NM - 1 - m + f) & (NM - 1), mb = (NM - 1 - m + f + 32) & (NM - 1);   // band 127 - m
+        const pk2 r0 = pk(xa0[ca], xb0[cb]), r1 = pk(xa1[ca], xb1[cb]);
+        const pk2 t0 = pk(xa0[ma], xb0[mb]), t1 = pk(xa1[ma], xb1[mb]);
         const pk2 d0 = max2(r0, fl0), d1 = max2(r1, fl1), d2 = max2(r1 - splat(kDbQuarter), fl2);
+        const pk2 u0 = max2(t0, fl0), u1 = max2(t1, fl1), u2 = max2(t1 - splat(kDbQuarter), fl2);
+        const pk2 e[3] = {d0 + u0, d1 + u1, d2 + u2}, o[3] = {d0 - u0, d1 - u1, d2 - u2};
         const float2 w01 = *reinterpret_cast<const float2*>(drow + m * DS);
         const float2 w23 = *reinterpret_cast<const float2*>(drow + m * DS + 2);
         const float2 w45 = *reinterpret_cast<const float2*>(drow + m * DS + 4);
@@ -529,11 +538,10 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
         const float2 w89 = *reinterpret_cast<const float2*>(drow + m * DS + 8);
         const float w[10] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w89.x, w89.y};
 #pragma unroll
-        for (int c = 0; c < 10; ++c) {
+        for (int c = 0; c < 10; ++c) {                                               // 10 q is even: coefficient parity = c parity
             const pk2 wc = splat(w[c]);
-            acc[0][c] = fma2(d0, wc, acc[0][c]);
-            acc[1][c] = fma2(d1, wc, acc[1][c]);
-            acc[2][c] = fma2(d2, wc, acc[2][c]);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) acc[s][c] = fma2((c & 1) ? o[s] : e[s], wc, acc[s][c]);
         }
     }
 #pragma unroll
@@ -545,11 +553,11 @@ __global__ void __launch_bounds__(kDctThreads) mfcc_dct_kernel(const MfccDctPara
         const long long f0 = prm.frame_off[u];
         const int T = (int)(prm.frame_off[u + 1] - f0);
         const int t = (int)(g - f0);
-        float* o = prm.out + f0 * (3 * NC) + t;
+        float* out = prm.out + f0 * (3 * NC) + t;
 #pragma unroll
         for (int s = 0; s < 3; ++s)
 #pragma unroll
-            for (int c = 0; c < 10; ++c) o[(long long)(s * NC + 10 * q + c) * T] = half ? hi(acc[s][c]) : lo(acc[s][c]);
+            for (int c = 0; c < 10; ++c) out[(long long)(s * NC + 10 * q + c) * T] = half ? hi(acc[s][c]) : lo(acc[s][c]);
     }
 }
 
