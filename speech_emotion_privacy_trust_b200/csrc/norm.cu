@@ -16,6 +16,26 @@
 
 namespace sept {
 
+// floor(a / d) for 0 <= a < 2^22 through a float reciprocal (inv = 1.0f / d) and one correction step: exact, and a
+// handful of instructions where the integer division costs ~20 -- the statistics kernel was issue bound on it
+__device__ __forceinline__ int div_floor_small(int a, int d, float inv) {
+    int q = (int)((float)a * inv);
+    const int r = a - q * d;
+    if (r >= d) ++q;
+    else if (r < 0) --q;
+    return q;
+}
+
+// the same weight with the divisions by `shift` done by div_floor_small; n_win = (T - win) / shift + 1 is passed in
+__device__ __forceinline__ int frame_weight_fast(int t, int T, int win, int shift, float inv_shift, int n_win, bool whole) {
+    if (whole || T < win) return 1;
+    int i_hi = div_floor_small(t, shift, inv_shift);
+    if (i_hi > n_win - 1) i_hi = n_win - 1;
+    const int num = t - win + 1;
+    const int i_lo = num <= 0 ? 0 : div_floor_small(num + shift - 1, shift, inv_shift);
+    return i_hi >= i_lo ? i_hi - i_lo + 1 : 0;
+}
+
 // number of training windows (start i*shift, length win) that contain frame t of a T-frame utterance (:44-48)
 __device__ __forceinline__ int frame_weight(int t, int T, int win, int shift, bool whole) {
     if (whole || T < win) return 1;
@@ -86,13 +106,15 @@ __global__ void __launch_bounds__(256) utt_partial128_kernel(const SpeakerStatsP
     float n = 0.f;
     float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), m2 = mean;
     float4 mn = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX), mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    const float inv_shift = 1.0f / (float)p.shift_len;
+    const int n_win = T >= p.win_len ? (T - p.win_len) / p.shift_len + 1 : 0;
     for (int t = warp; t < T; t += 4 * WARPS) {
         float4 x[4];
         int w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int tt = t + j * WARPS;
-            w[j] = tt < T ? frame_weight(tt, T, p.win_len, p.shift_len, whole) : 0;
+            w[j] = tt < T ? frame_weight_fast(tt, T, p.win_len, p.shift_len, inv_shift, n_win, whole) : 0;
             if (w[j]) x[j] = rows[(long long)tt * (F / 4)];
         }
 #pragma unroll
@@ -100,7 +122,7 @@ __global__ void __launch_bounds__(256) utt_partial128_kernel(const SpeakerStatsP
             if (!w[j]) continue;
             const float wf = (float)w[j];
             n += wf;
-            const float r = wf / n;
+            const float r = __fdividef(wf, n);                    // 2 ulp; n <= 4 T, far from the fast division's range limit
             welford_add(mean.x, m2.x, mn.x, mx.x, x[j].x, wf, r);
             welford_add(mean.y, m2.y, mn.y, mx.y, x[j].y, wf, r);
             welford_add(mean.z, m2.z, mn.z, mx.z, x[j].z, wf, r);
