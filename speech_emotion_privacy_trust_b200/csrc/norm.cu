@@ -250,15 +250,33 @@ __global__ void __launch_bounds__(256) normalize4_kernel(const NormalizeParams p
     if (r0 >= rows_per_pass) return;
     const float4 mean = reinterpret_cast<const float4*>(st + p.n_feat)[q], sd = reinterpret_cast<const float4*>(st + 2 * p.n_feat)[q];
     const float4 mn = reinterpret_cast<const float4*>(st + 3 * p.n_feat)[q], mx = reinterpret_cast<const float4*>(st + 4 * p.n_feat)[q];
-    for (int r = r0; r < rows; r += rows_per_pass) {
-        const int t = t_begin + r;
-        const float4 x = t < T ? in[(long long)t * F4 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 z;
-        z.x = normalize_one(x.x, mean.x, sd.x, mn.x, mx.x, p.mode);
-        z.y = normalize_one(x.y, mean.y, sd.y, mn.y, mx.y, p.mode);
-        z.z = normalize_one(x.z, mean.z, sd.z, mn.z, mx.z, p.mode);
-        z.w = normalize_one(x.w, mean.w, sd.w, mn.w, mx.w, p.mode);
-        out[(long long)r * F4 + q] = z;
+    // z = (x - a) * b + c with the divisions done once per thread: znorm a = mean, b = 1 / (std + 1e-5), c = 0;
+    // min_max a = min, b = 2 / (max - min), c = -1.  Four rows are in flight per thread.
+    float4 a, b;
+    float c;
+    if (p.mode == 0) {
+        a = mean; c = 0.f;
+        b = make_float4(1.0f / (sd.x + 1e-5f), 1.0f / (sd.y + 1e-5f), 1.0f / (sd.z + 1e-5f), 1.0f / (sd.w + 1e-5f));
+    } else {
+        a = mn; c = -1.f;
+        b = make_float4(2.0f / (mx.x - mn.x), 2.0f / (mx.y - mn.y), 2.0f / (mx.z - mn.z), 2.0f / (mx.w - mn.w));
+    }
+    for (int r = r0; r < rows; r += 4 * rows_per_pass) {
+        float4 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rr = r + j * rows_per_pass, t = t_begin + rr;
+            x[j] = (rr < rows && t < T) ? in[(long long)t * F4 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rr = r + j * rows_per_pass;
+            if (rr >= rows) break;
+            float4 z;
+            z.x = fmaf(x[j].x - a.x, b.x, c); z.y = fmaf(x[j].y - a.y, b.y, c);
+            z.z = fmaf(x[j].z - a.z, b.z, c); z.w = fmaf(x[j].w - a.w, b.w, c);
+            out[(long long)rr * F4 + q] = z;
+        }
     }
 }
 
