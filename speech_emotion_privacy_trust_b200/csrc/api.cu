@@ -56,6 +56,9 @@ struct ResampleConsts {
     int32_t* k_lo = nullptr;
     float* w = nullptr;
     int taps = 0, width = 0;
+    int32_t* tile_base = nullptr;
+    float* tile_wt = nullptr;
+    int n_groups = 0, tg = 0, base_min = 0, base_max = 0;
 };
 
 std::map<std::tuple<int, int, int>, ResampleConsts> g_resample;
@@ -132,6 +135,11 @@ int get_resample(int orig, int up, ResampleConsts* out) {
         c.width = sept::make_resample_rows(orig, up, k_lo, rows, c.taps);
         SEPT_CUDA(upload(k_lo, &c.k_lo));
         SEPT_CUDA(upload(rows, &c.w));
+        sept::ResampleTiles tiles;
+        sept::make_resample_tiles(up, c.taps, k_lo, rows, tiles);
+        SEPT_CUDA(upload(tiles.base, &c.tile_base));
+        SEPT_CUDA(upload(tiles.wt, &c.tile_wt));
+        c.n_groups = tiles.n_groups; c.tg = tiles.tg; c.base_min = tiles.base_min; c.base_max = tiles.base_max;
         it = g_resample.emplace(key, c).first;
     }
     *out = it->second;
@@ -276,6 +284,11 @@ int sept_resample_f32(const float* in, const int64_t* in_off, const int64_t* out
     sept::ResampleParams p{};
     p.in = in; p.in_off = in_off; p.out_off = out_off; p.n_utts = n_utts; p.orig = (int)orig; p.up = (int)up;
     p.width = c.width; p.taps = c.taps; p.k_lo = c.k_lo; p.w = c.w; p.out = out; p.total_out = total_out;
+    static const bool simple_only = getenv("SEPT_RESAMPLE_SIMPLE") != nullptr;   // A/B and tests of the fallback kernel
+    if (!simple_only) {
+        p.tile_base = c.tile_base; p.tile_wt = c.tile_wt; p.n_groups = c.n_groups; p.tg = c.tg;
+        p.base_min = c.base_min; p.base_max = c.base_max;
+    }
     SEPT_CUDA(sept::launch_resample(p, static_cast<cudaStream_t>(stream)));
     return SEPT_OK;
 }

@@ -17,6 +17,10 @@ struct ResampleParams {
     const float* w;             // [up][taps] kernel rows restricted to their non-zero support
     float* out;
     long long total_out;
+    // register-tile tables (tables.h: make_resample_tiles); tile_wt null: only the one-thread-per-sample kernel is available
+    const int32_t* tile_base;   // [n_groups]
+    const float* tile_wt;       // [n_groups][tg][4]
+    int n_groups, tg, base_min, base_max;
 };
 
 cudaError_t launch_resample(const ResampleParams& p, cudaStream_t stream);

@@ -268,4 +268,39 @@ inline int make_resample_rows(int orig, int up, std::vector<int32_t>& k_lo, std:
     return width;
 }
 
+
+// Register-tile form of the same rows for the tiled resampling kernel: phases are grouped four at a time; group g reads
+// the input window that starts at tap base[g] = min k_lo of its phases and is TG taps long (TG odd: conflict-free 16-byte
+// reads), and wt[(g * TG + i) * 4 + jj] is the weight of phase 4 g + jj at window position i (zero outside the phase's own
+// support, and for the phases past `up` in the last group).
+struct ResampleTiles {
+    std::vector<int32_t> base;   // [n_groups]
+    std::vector<float> wt;       // [n_groups][TG][4]
+    int n_groups = 0, tg = 0, base_min = 0, base_max = 0;
+};
+
+inline void make_resample_tiles(int up, int taps, const std::vector<int32_t>& k_lo, const std::vector<float>& rows, ResampleTiles& t) {
+    t.n_groups = (up + 3) / 4;
+    t.base.assign(t.n_groups, 0);
+    int span = 0;
+    for (int g = 0; g < t.n_groups; ++g) {
+        int lo = k_lo[4 * g], hi = lo;
+        for (int j = 4 * g; j < 4 * g + 4 && j < up; ++j) { if (k_lo[j] < lo) lo = k_lo[j]; if (k_lo[j] > hi) hi = k_lo[j]; }
+        t.base[g] = lo;
+        if (hi - lo > span) span = hi - lo;
+    }
+    t.tg = (taps + span) | 1;
+    t.wt.assign((size_t)t.n_groups * t.tg * 4, 0.f);
+    t.base_min = t.base[0]; t.base_max = t.base[0];
+    for (int g = 0; g < t.n_groups; ++g) {
+        if (t.base[g] < t.base_min) t.base_min = t.base[g];
+        if (t.base[g] > t.base_max) t.base_max = t.base[g];
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * g + jj;
+            if (j >= up) continue;
+            for (int k = 0; k < taps; ++k) t.wt[((size_t)g * t.tg + (k_lo[j] - t.base[g]) + k) * 4 + jj] = rows[(size_t)j * taps + k];
+        }
+    }
+}
+
 }  // namespace sept

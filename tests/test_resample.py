@@ -24,7 +24,8 @@ def test_oracle_matches_torchaudio_golden():
     assert [len(restate.resample(np.zeros(n), 44100, 16000)) for n in (1, 441, 442, 44100)] == [1, 160, 161, 16000]
 
 
-@pytest.mark.parametrize("orig,up,rates", [(441, 160, (44100, 16000)), (3, 1, (48000, 16000)), (1, 2, (8000, 16000))])
+@pytest.mark.parametrize("orig,up,rates", [(441, 160, (44100, 16000)), (3, 1, (48000, 16000)), (1, 2, (8000, 16000)),
+                                           (147, 160, (44100, 48000)), (160, 441, (16000, 44100))])
 def test_library_row_table_matches_oracle_kernel(tmp_path, orig, up, rates):
     exe = tmp_path / "rows"
     subprocess.run(["g++", "-O1", "-std=c++17", "-I", str(REPO / "speech_emotion_privacy_trust_b200" / "csrc"),
@@ -72,3 +73,14 @@ def test_cuda_resampler_vs_golden_and_oracle():
         strong = ref > ref.max(axis=0, keepdims=True) - 50.0
         assert got.shape == ref.shape and np.max(np.abs(got - ref)[strong]) < 1e-3
     assert extraction.resample(r, 16000, 16000) is r
+    # other rate pairs (other tile shapes of the tiled kernel; utterance boundaries inside a CTA's sample range)
+    rng = np.random.default_rng(13)
+    for f_in, f_out in ((44100, 48000), (16000, 44100), (8000, 16000), (22050, 16000)):
+        ws = [(0.3 * rng.standard_normal(int(n))).astype(np.float32) for n in (977, 12001, 1, 3333, 40, 20011)]
+        res = extraction.resample(extraction.RaggedAudio.from_list(ws), f_in, f_out)
+        o = res.utt_off_host
+        for u, w in enumerate(ws):
+            ref = restate.resample(w, f_in, f_out)
+            got = res.wav[o[u]:o[u + 1]].cpu().numpy()
+            assert got.shape == ref.shape, (f_in, f_out, u)
+            assert np.max(np.abs(got - ref)) < TOL, (f_in, f_out, u)
