@@ -142,7 +142,7 @@ def split_band_major(flat: torch.Tensor, lay: Layout, rows: int) -> list[torch.T
 
 # ---- host-buffer entry point: copies pipelined against the kernel ----------------------------------------------
 def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 800, n_mels: int = 128, hop: int = HOP_MEL,
-                out_host: torch.Tensor | None = None, device="cuda", chunk_samples: int = 1 << 25, n_streams: int = 3):
+                out_host: torch.Tensor | None = None, device="cuda", chunk_samples: int = 1 << 24, n_streams: int = 3):
     """log-mel dB for a ragged batch that lives in HOST memory, result back in host memory (frame-major).
 
     wav_host may also be 16-bit PCM (int16): it is converted on the device as x / 32768, exactly what torchaudio.load does
