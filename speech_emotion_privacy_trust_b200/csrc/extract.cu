@@ -1,10 +1,12 @@
 // Fused speech feature extraction kernels for sm_100a (see extract_core.cuh for the per-lane phases).
 //
-//   extract_kernel<R, MODE>   persistent, one CTA per SM; each WARP walks its share of the items (an item = FPW
+//   extract_kernel<R, MODE, FAST>  persistent, one CTA per SM; each WARP walks its share of the items (an item = FPW
 //                             consecutive frames of one utterance) through stage -> window+DFT25 -> DFT-R ->
-//                             real split+power -> sparse mel -> log, touching HBM only for the waveform span
-//                             and the finished features.
-//   mfcc_dct_kernel           second phase of MFCC: per-utterance top_db floor + ortho DCT-II.
+//                             real split+power -> mel gather program -> log, touching HBM only for the waveform span
+//                             and the finished features.  FAST (the reference's 128-band filterbank): the lane-constant
+//                             tables -- window samples, split twiddles, mel program -- live in tensor memory (tmem.cuh)
+//                             and the mel phase is unrolled; otherwise they are read from shared memory.
+//   mfcc_dct_kernel           second phase of MFCC: per-utterance top_db floor + ortho DCT-II (folded, frame pairs).
 //
 // Replaces torchaudio MelSpectrogram/AmplitudeToDB/MFCC as called by
 // feature_extraction/audio_feature_extraction.py:15-46 of the reference.

@@ -13,11 +13,12 @@
 // Warp-private shared memory:
 //   stage  float [2 + SPAN + 1], SPAN = (FPW-1)*hop + n_fft   reflect-padded waveform span of the item at offset 2,
 //                                                one halo sample either side (for the waveform-gradient stream)
-//   Y      pk2   [PPW][25 rows k2][re: R | im: R | pad 2]   pass 1 output / pass 2 input; each pk2 = (frame a, frame b).
+//   Y      pk2   [PPW][25 (+1) rows k2][re: R | im: R | pad 2]   pass 1 output / pass 2 input; each pk2 = (frame a, frame b);
+//                                                the fused pass keeps a second copy of row 0 in row 25.
 //                                                Real and imaginary parts sit in separate half rows so that their
 //                                                8-byte stores cannot be fused into quads (which costs 4 MOVs each)
 //   P      pk2   [PPW][PP] over the Y tile       4|X[k]|^2 of the frame pair at bin_pos(k) (written only after every Z
-//                                                of the item has been read into registers)
+//                                                of the item has been read into registers), then three zero slots
 // Replaces, for one item: torch.stft framing/window/rFFT + abs().pow(2) (torchaudio functional.py:123-144)
 // and MelScale's matmul (transforms/_transforms.py:417).
 #pragma once
