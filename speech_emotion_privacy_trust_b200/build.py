@@ -39,11 +39,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
     nvcc = _nvcc()
+    extra = os.environ.get("SEPT_NVCC_EXTRA", "").split()        # experiments only (compiler flag A/B)
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
     procs = []
     for src in SOURCES:
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(objdir / (src + ".o"))]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(objdir / (src + ".o"))]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
