@@ -444,13 +444,13 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 
 // ---- MFCC phase 2: dB with the per-utterance floor, then DCT (transforms/_transforms.py:714-717) ------------
 // One CTA handles kDctFrames = 64 consecutive global frames (they may straddle utterances).  The load phase converts the
-// two mel-power streams to dB in shared memory (unclamped).  Thread (f = tid % 32, q = tid / 32) then produces
+// two mel-power streams to dB in shared memory, clamped at the top_db floor of their utterance.  Thread (f = tid % 32, q = tid / 32) then produces
 // coefficients [10q, 10q+10) of the three streams for the frame PAIR (f, f + 32) packed in pk2 (30 packed accumulators;
 // the weights are fetched once per two frames).  The ortho DCT-II basis is symmetric, D[127-m][c] = (-1)^c D[m][c], so
 // bands m and 127-m are folded first: even coefficients take x[m] + x[127-m], odd ones the difference -- 15 + 15 FFMA2
-// per band pair instead of 60, and only half of the basis in shared memory.  The top_db floors are applied on the fly;
-// stream 2 (np.gradient(x, 2) == np.gradient(x) / 2 exactly, a quarter of stream 1's power) is stream 1's dB minus
-// 10 log10(4), with amplitude_to_DB's amin clamp (-100 dB) folded into its floor.  Rows of the dB tile are rotated by the
+// per band pair instead of 60, and only half of the basis in shared memory.  Stream 2 (np.gradient(x, 2) ==
+// np.gradient(x) / 2 exactly, a quarter of stream 1's power) is derived on the fly: its dB and its floor are stream 1's
+// minus 10 log10(4), so it is the clamped stream 1 minus 10 log10(4), clamped again at amplitude_to_DB's amin (-100 dB).  Rows of the dB tile are rotated by the
 // frame index instead of padded (conflict-free scalar reads, exactly 64 KB), which lets three CTAs share an SM.
 constexpr int kDctFrames = 64;
 constexpr int kDctThreads = 128;
@@ -497,14 +497,16 @@ __global__ void __launch_bounds__(kDctThreads, 3) mfcc_dct_kernel(const MfccDctP
                              ? __ldg(reinterpret_cast<const float4*>(prm.power + ((long long)s * prm.total_frames + g) * NM) + m4)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (pass == 0) __syncthreads();                                          // frame_floor is ready (the loads are in flight)
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int combo = (pass * NIT + it) * 4 + warp, s = combo >> 6, rem = combo & 63;
                 const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
                 float* x = X + (s * kDctFrames + f) * NM;
                 const int col = 4 * m4 + f;
-                x[col & (NM - 1)] = power_to_db(pw[it].x); x[(col + 1) & (NM - 1)] = power_to_db(pw[it].y);
-                x[(col + 2) & (NM - 1)] = power_to_db(pw[it].z); x[(col + 3) & (NM - 1)] = power_to_db(pw[it].w);
+                const float fl = frame_floor[s * kDctFrames + f];                    // top_db floor of the frame's utterance
+                x[col & (NM - 1)] = fmaxf(power_to_db(pw[it].x), fl); x[(col + 1) & (NM - 1)] = fmaxf(power_to_db(pw[it].y), fl);
+                x[(col + 2) & (NM - 1)] = fmaxf(power_to_db(pw[it].z), fl); x[(col + 3) & (NM - 1)] = fmaxf(power_to_db(pw[it].w), fl);
             }
         }
     }
@@ -519,9 +521,6 @@ __global__ void __launch_bounds__(kDctThreads, 3) mfcc_dct_kernel(const MfccDctP
     const float* xb0 = xa0 + 32 * NM;                                                // frame f + 32 (rotated by f + 32)
     const float* xa1 = xa0 + kDctFrames * NM;
     const float* xb1 = xb0 + kDctFrames * NM;
-    const pk2 fl0 = pk(frame_floor[f], frame_floor[f + 32]);
-    const pk2 fl1 = pk(frame_floor[kDctFrames + f], frame_floor[kDctFrames + f + 32]);
-    const pk2 fl2 = pk(frame_floor[2 * kDctFrames + f], frame_floor[2 * kDctFrames + f + 32]);
     const float* drow = D + 10 * q;
     auto max2 = [](pk2 a, pk2 b) { return pk(fmaxf(lo(a), lo(b)), fmaxf(hi(a), hi(b))); };
 #pragma unroll 2
@@ -530,8 +529,10 @@ __global__ void __launch_bounds__(kDctThreads, 3) mfcc_dct_kernel(const MfccDctP
         const int ma = (NM - 1 - m + f) & (NM - 1), mb = (NM - 1 - m + f + 32) & (NM - 1);   // band 127 - m
         const pk2 r0 = pk(xa0[ca], xb0[cb]), r1 = pk(xa1[ca], xb1[cb]);
         const pk2 t0 = pk(xa0[ma], xb0[mb]), t1 = pk(xa1[ma], xb1[mb]);
-        const pk2 d0 = max2(r0, fl0), d1 = max2(r1, fl1), d2 = max2(r1 - splat(kDbQuarter), fl2);
-        const pk2 u0 = max2(t0, fl0), u1 = max2(t1, fl1), u2 = max2(t1 - splat(kDbQuarter), fl2);
+        // streams 0 and 1 were clamped in the load phase; stream 2 = max(dB1 - 10 log10 4, floor1 - 10 log10 4, -100)
+        //                                                           = max(clamped dB1 - 10 log10 4, -100)
+        const pk2 d0 = r0, d1 = r1, d2 = max2(r1 - splat(kDbQuarter), splat(-100.0f));
+        const pk2 u0 = t0, u1 = t1, u2 = max2(t1 - splat(kDbQuarter), splat(-100.0f));
         const pk2 e[3] = {d0 + u0, d1 + u1, d2 + u2}, o[3] = {d0 - u0, d1 - u1, d2 - u2};
         const float2 w01 = *reinterpret_cast<const float2*>(drow + m * DS);
         const float2 w23 = *reinterpret_cast<const float2*>(drow + m * DS + 2);
