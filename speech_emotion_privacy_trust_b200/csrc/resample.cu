@@ -78,7 +78,7 @@ __host__ __device__ inline TileGeom resample_tile_geom(int orig, int n_groups, i
     TileGeom g;
     g.rows_per_cta = 4 * mg;
     // rows m_lo .. m_lo + 4 (mg + 1) - 1 can be touched (a CTA's sample range need not start on a row boundary)
-    g.stage_floats = ((4 * (mg + 1) - 1) * orig + (base_max - base_min) + tg + 4) & ~3;
+    g.stage_floats = ((4 * (mg + 1) - 1) * orig + (base_max - base_min) + tg + 3 + 4) & ~3;   // + 3: 16-byte aligned fill
     return g;
 }
 
@@ -129,13 +129,20 @@ __global__ void __launch_bounds__(kTileThreads) resample_tiled_kernel(const Resa
         const long long s0 = m_lo * p.orig + p.base_min - p.width;                    // input index of stage[0]
         const int n_stage = (4 * n_mg - 1) * p.orig + (p.base_max - p.base_min) + p.tg;
         __syncthreads();                                                              // the previous segment's reads are done
-        const float* src = p.in + in0 + s0;
-        if (s0 >= 0 && s0 + n_stage <= n_in) {                                        // interior: no bounds tests, 8 loads in flight
-#pragma unroll 8
-            for (int i = threadIdx.x; i < n_stage; i += kTileThreads) stage[i] = __ldg(src + i);
+        // the span is staged from the 16-byte boundary below its first sample (`shift` floats earlier), so that an
+        // interior span moves with 16-byte loads; stage[shift + i] is input sample s0 + i
+        const float* src0 = p.in + in0 + s0;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(src0) >> 2) & 3);
+        const float* src = src0 - shift;
+        const int n_fill = n_stage + shift;
+        if (s0 - shift >= 0 && s0 - shift + ((n_fill + 3) & ~3) <= n_in) {            // interior: no bounds tests, 16-byte loads
+            const float4* src4 = reinterpret_cast<const float4*>(src);
+            float4* dst4 = reinterpret_cast<float4*>(stage);
+#pragma unroll 4
+            for (int i = threadIdx.x; i < (n_fill + 3) / 4; i += kTileThreads) dst4[i] = __ldg(src4 + i);
         } else {
-            for (int i = threadIdx.x; i < n_stage; i += kTileThreads) {
-                const long long idx = s0 + i;
+            for (int i = threadIdx.x; i < n_fill; i += kTileThreads) {
+                const long long idx = s0 - shift + i;
                 stage[i] = (idx >= 0 && idx < n_in) ? __ldg(src + i) : 0.f;
             }
         }
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(kTileThreads) resample_tiled_kernel(const Resa
         for (int tile = threadIdx.x; tile < n_mg * p.n_groups; tile += kTileThreads) {
             const int g = tile % p.n_groups, mg = tile / p.n_groups;
             const float4* w = wt + g * p.tg;
-            const float* x0 = stage + (4 * mg) * p.orig + (base[g] - p.base_min);
+            const float* x0 = stage + shift + (4 * mg) * p.orig + (base[g] - p.base_min);
             const float* x1 = x0 + p.orig;
             const float* x2 = x1 + p.orig;
             const float* x3 = x2 + p.orig;
