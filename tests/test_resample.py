@@ -84,3 +84,24 @@ def test_cuda_resampler_vs_golden_and_oracle():
             got = res.wav[o[u]:o[u + 1]].cpu().numpy()
             assert got.shape == ref.shape, (f_in, f_out, u)
             assert np.max(np.abs(got - ref)) < TOL, (f_in, f_out, u)
+
+
+@pytest.mark.gpu
+def test_cuda_simple_kernel_fallback_in_a_fresh_process():
+    """Rate pairs whose tables do not fit shared memory take the one-thread-per-sample kernel; SEPT_RESAMPLE_SIMPLE=1 (read
+    once per process) forces it, so the same golden comparison runs in a child process with the variable set."""
+    import os
+    import sys
+    code = (
+        "import numpy as np, sys\n"
+        f"sys.path.insert(0, {str(REPO)!r})\n"
+        "from speech_emotion_privacy_trust_b200 import extraction\n"
+        f"g = np.load({str(REPO / 'tests' / 'golden' / 'resample.npz')!r})\n"
+        "b = extraction.RaggedAudio.from_list([g[f'in{i}'] for i in range(4)])\n"
+        "o = extraction.resample(b, 44100, 16000); off = o.utt_off_host\n"
+        "err = max(float(np.max(np.abs(o.wav[off[i]:off[i+1]].cpu().numpy() - g[f'out{i}']))) for i in range(4))\n"
+        "print('ERR', err)\n")
+    env = dict(os.environ, SEPT_RESAMPLE_SIMPLE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert float(r.stdout.split("ERR")[1]) < TOL
