@@ -82,23 +82,31 @@ __host__ __device__ inline TileGeom resample_tile_geom(int orig, int n_groups, i
     return g;
 }
 
-__global__ void __launch_bounds__(kTileThreads) resample_tiled_kernel(const ResampleParams p) {
+// A CTA is two independent halves of kTileThreads threads that share the weight table and each walk their own chunk
+// range with their own stage and their own named barrier: a third more resident warps for the same shared memory.
+__device__ __forceinline__ void half_barrier(int half) { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kTileThreads) : "memory"); }
+
+__global__ void __launch_bounds__(2 * kTileThreads) resample_tiled_kernel(const ResampleParams p) {
+    const int half = threadIdx.x / kTileThreads, tid = threadIdx.x % kTileThreads;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     float4* wt = reinterpret_cast<float4*>(rs_smem);                                  // [n_groups][tg]
     int* base = reinterpret_cast<int*>(wt + p.n_groups * p.tg);                       // [n_groups]
-    float* stage = reinterpret_cast<float*>(base + ((p.n_groups + 3) & ~3));
-    __shared__ int u_first;
     const TileGeom geo = resample_tile_geom(p.orig, p.n_groups, p.tg, p.base_min, p.base_max);
+    float* stage = reinterpret_cast<float*>(base + ((p.n_groups + 3) & ~3)) + half * geo.stage_floats;
+    __shared__ int u_first_sh[2];
+    int& u_first = u_first_sh[half];
     const long long per_cta = (long long)geo.rows_per_cta * p.up;
-    for (int i = threadIdx.x; i < p.n_groups * p.tg; i += kTileThreads) wt[i] = reinterpret_cast<const float4*>(p.tile_wt)[i];
-    for (int i = threadIdx.x; i < p.n_groups; i += kTileThreads) base[i] = p.tile_base[i];
+    for (int i = threadIdx.x; i < p.n_groups * p.tg; i += 2 * kTileThreads) wt[i] = reinterpret_cast<const float4*>(p.tile_wt)[i];
+    for (int i = threadIdx.x; i < p.n_groups; i += 2 * kTileThreads) base[i] = p.tile_base[i];
+    __syncthreads();
     // persistent CTAs: the weight table is fetched once, then the CTA walks over its CONTIGUOUS range of chunks of
     // rows_per_cta * up samples -- the utterance of a chunk's first sample is found by one binary search per CTA and a
     // short forward walk per chunk (a search per chunk, ten dependent global loads by one thread, cost more than the
     // chunk's arithmetic)
     const long long n_chunks = (p.total_out + per_cta - 1) / per_cta;
-    const long long c_begin = n_chunks * blockIdx.x / gridDim.x, c_end = n_chunks * (blockIdx.x + 1) / gridDim.x;
-    if (threadIdx.x == 0) {
+    const long long n_workers = 2LL * gridDim.x, worker = 2LL * blockIdx.x + half;
+    const long long c_begin = n_chunks * worker / n_workers, c_end = n_chunks * (worker + 1) / n_workers;
+    if (tid == 0) {
         const long long g_first = c_begin * per_cta;
         int lo = 0, hi = p.n_utts - 1;
         while (lo < hi) {
@@ -111,13 +119,13 @@ __global__ void __launch_bounds__(kTileThreads) resample_tiled_kernel(const Resa
     const long long g0 = chunk * per_cta;
     long long g1 = g0 + per_cta;
     if (g1 > p.total_out) g1 = p.total_out;
-    __syncthreads();                                                                  // u_first is set / the previous chunk is done
-    if (threadIdx.x == 0) {
+    half_barrier(half);                                                                  // u_first is set / the previous chunk is done
+    if (tid == 0) {
         int u = u_first;
         while (u < p.n_utts - 1 && p.out_off[u + 1] <= g0) ++u;
         u_first = u;
     }
-    __syncthreads();
+    half_barrier(half);
     for (int u = u_first; u < p.n_utts && p.out_off[u] < g1; ++u) {
         const long long oo = p.out_off[u], n_out = p.out_off[u + 1] - oo;
         if (n_out <= 0) continue;
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(kTileThreads) resample_tiled_kernel(const Resa
         const long long in0 = p.in_off[u], n_in = p.in_off[u + 1] - in0;
         const long long s0 = m_lo * p.orig + p.base_min - p.width;                    // input index of stage[0]
         const int n_stage = (4 * n_mg - 1) * p.orig + (p.base_max - p.base_min) + p.tg;
-        __syncthreads();                                                              // the previous segment's reads are done
+        half_barrier(half);                                                              // the previous segment's reads are done
         // the span is staged from the 16-byte boundary below its first sample (`shift` floats earlier), so that an
         // interior span moves with 16-byte loads; stage[shift + i] is input sample s0 + i
         const float* src0 = p.in + in0 + s0;
@@ -139,15 +147,15 @@ __global__ void __launch_bounds__(kTileThreads) resample_tiled_kernel(const Resa
             const float4* src4 = reinterpret_cast<const float4*>(src);
             float4* dst4 = reinterpret_cast<float4*>(stage);
 #pragma unroll 4
-            for (int i = threadIdx.x; i < (n_fill + 3) / 4; i += kTileThreads) dst4[i] = __ldg(src4 + i);
+            for (int i = tid; i < (n_fill + 3) / 4; i += kTileThreads) dst4[i] = __ldg(src4 + i);
         } else {
-            for (int i = threadIdx.x; i < n_fill; i += kTileThreads) {
+            for (int i = tid; i < n_fill; i += kTileThreads) {
                 const long long idx = s0 - shift + i;
                 stage[i] = (idx >= 0 && idx < n_in) ? __ldg(src + i) : 0.f;
             }
         }
-        __syncthreads();
-        for (int tile = threadIdx.x; tile < n_mg * p.n_groups; tile += kTileThreads) {
+        half_barrier(half);
+        for (int tile = tid; tile < n_mg * p.n_groups; tile += kTileThreads) {
             const int g = tile % p.n_groups, mg = tile / p.n_groups;
             const float4* w = wt + g * p.tg;
             const float* x0 = stage + shift + (4 * mg) * p.orig + (base[g] - p.base_min);
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(kTileThreads) resample_tiled_kernel(const Resa
 
 static size_t resample_tiled_smem(const ResampleParams& p) {
     const TileGeom geo = resample_tile_geom(p.orig, p.n_groups, p.tg, p.base_min, p.base_max);
-    return (size_t)p.n_groups * p.tg * 16 + (size_t)((p.n_groups + 3) & ~3) * 4 + (size_t)geo.stage_floats * 4;
+    return (size_t)p.n_groups * p.tg * 16 + (size_t)((p.n_groups + 3) & ~3) * 4 + 2 * (size_t)geo.stage_floats * 4;
 }
 
 // 16-bit PCM -> float in [-1, 1): x / 32768, what torchaudio.load(normalize=True) does on the host before the reference's
@@ -213,15 +221,15 @@ cudaError_t launch_resample(const ResampleParams& p, cudaStream_t stream) {
     if (p.total_out <= 0) return cudaSuccess;
     if (p.tile_wt) {
         const size_t smem = resample_tiled_smem(p);
-        if (smem <= 100 * 1024) {                                  // two CTAs per SM at least; larger tables take the simple kernel
+        if (smem <= 112 * 1024) {                                  // two CTAs per SM at least; larger tables take the simple kernel
             const TileGeom geo = resample_tile_geom(p.orig, p.n_groups, p.tg, p.base_min, p.base_max);
             const long long per_cta = (long long)geo.rows_per_cta * p.up;
             long long blocks = (p.total_out + per_cta - 1) / per_cta;
-            const long long resident = 148LL * (smem <= 72 * 1024 ? 3 : 2);
+            const long long resident = 148LL * (smem <= 72 * 1024 ? 3 : 2);   // CTAs of two independent halves
             if (blocks > resident) blocks = resident;              // persistent: the weight table is loaded once per CTA
             cudaError_t e = cudaFuncSetAttribute(resample_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            resample_tiled_kernel<<<(unsigned)blocks, kTileThreads, smem, stream>>>(p);
+            resample_tiled_kernel<<<(unsigned)blocks, 2 * kTileThreads, smem, stream>>>(p);
             return cudaGetLastError();
         }
     }
