@@ -22,17 +22,9 @@ def build_model(dev, grl_lambda=0.1, seed=8):
     return cloak_models.two_d_cnn_lstm_syn_with_grl(mk("emotion"), mk("gender"), noise, grl_lambda).to(dev)
 
 
-def weighted_losses(p_emo, p_gen, emo, gen, w, gender_lambda):
-    """sum_i CE(emotion_i) * w_i / B + gender_lambda * CE(gender_i) * w_i / B  (reference :141-154, one launch per term
-    instead of 2B)."""
-    ce = torch.nn.functional.cross_entropy
-    b = p_emo.shape[0]
-    return ((ce(p_emo, emo, reduction="none") + gender_lambda * ce(p_gen, gen, reduction="none")) * w).sum() / b
-
-
 def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_last=True, graphs=True):
     import torch.distributed as dist
-    from speech_emotion_privacy_trust_b200 import parallel, synth
+    from speech_emotion_privacy_trust_b200 import losses, parallel, synth
     model = build_model(dev).train()
     if channels_last:
         # stock cuDNN picks its NHWC tensor-core convolutions and the fast NHWC batch-norm; the (B,1,200,128) input of
@@ -50,7 +42,7 @@ def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_la
 
     def loss_fn(m, xb, eb, gb, wb):
         p1, p2, _ = m(xb, pooling="mean")
-        return weighted_losses(p1, p2, eb, gb, wb, 0.1)
+        return losses.cloak_grl_loss(p1, p2, eb, gb, wb, 0.1)
 
     graphed = None
     if graphs:
@@ -147,7 +139,7 @@ def cloak_kernel_bandwidth(dev, batch=64, reps=64):
     locs, rhos = torch.zeros(wf, device=dev), torch.full((wf,), -2.0, device=dev)
     eps = 0.1 * torch.randn(wf, device=dev)
     lib = cloak_ops._lib.lib()
-    ws = cloak_ops._workspace(dev, wf)
+    ws = cloak_ops.new_workspace(dev, wf)
     outs = [torch.empty_like(xs[0]) for _ in range(sets)]
     dlocs, drhos = torch.empty(wf, device=dev), torch.empty(wf, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream

@@ -41,6 +41,9 @@ typedef void* sept_stream_t; /* cudaStream_t */
 
 int sept_version(void);
 const char* sept_last_error(void);
+/* "SEPT_SRC_HASH=<sha256 of the sources this library was compiled from>": the Python loader refuses (or rebuilds) a
+ * library whose hash differs from the sources next to it, so a stale prebuilt .so is never tested silently. */
+const char* sept_source_hash(void);
 
 /* Build the constant cache of the current device for n_fft in {400, 800, 1600} x n_mels, and the 128x40 DCT basis.
  * Optional (first use does it), but call it before CUDA-graph capture. */

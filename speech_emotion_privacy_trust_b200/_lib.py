@@ -15,6 +15,7 @@ c_ptr = C.c_void_p
 _SIGNATURES = {
     "sept_version": (C.c_int, []),
     "sept_last_error": (C.c_char_p, []),
+    "sept_source_hash": (C.c_char_p, []),
     "sept_init": (C.c_int, [C.c_int]),
     "sept_frames_per_item": (C.c_int, [C.c_int]),
     "sept_extract_layout": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
@@ -46,23 +47,34 @@ def library_path() -> Path:
 
 
 def lib() -> C.CDLL:
-    """Load libsept_b200.so; build it first (under a file lock: several ranks may start together) only if it is absent.
-    A stale library is rebuilt by `python -m speech_emotion_privacy_trust_b200.build` / __graft_entry__.build(), never
-    implicitly.  Raises if the library is missing and cannot be built -- there is no CPU fallback."""
+    """Load libsept_b200.so.  The library carries the sha256 of the sources it was compiled from; if it is absent or
+    that hash differs from the sources in the tree (a stale prebuilt .so), it is rebuilt first (under a file lock:
+    several ranks may start together), and if it cannot be rebuilt the call raises -- a stale library is never used
+    silently and there is no CPU fallback."""
     global _LIB
     if _LIB is None:
         import os
-        path = Path(os.environ["SEPT_LIB_PATH"]) if os.environ.get("SEPT_LIB_PATH") else _build.LIB   # experiments only
-        if not path.exists():
+        override = os.environ.get("SEPT_LIB_PATH")                 # experiments only (A/B of two builds): no hash check
+        path = Path(override) if override else _build.LIB
+        if not override and _build.stale():
             import fcntl
             with open(str(path) + ".lock", "w") as lock:
                 fcntl.flock(lock, fcntl.LOCK_EX)
-                if not path.exists():
-                    _build.build()
+                if _build.stale():
+                    try:
+                        _build.build(force=True)
+                    except RuntimeError as exc:
+                        state = "missing" if not path.exists() else "stale (built from other sources than the tree holds)"
+                        raise RuntimeError(f"{path.name} is {state} and cannot be rebuilt: {exc}") from exc
         handle = C.CDLL(str(path))
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
+        if not override:
+            got = handle.sept_source_hash().decode().split("=", 1)[1]
+            if got != _build.source_hash():
+                raise RuntimeError(f"{path.name} was built from other sources than the tree holds ({got[:12]} != "
+                                   f"{_build.source_hash()[:12]}); run python -m speech_emotion_privacy_trust_b200.build --force")
         _LIB = handle
     return _LIB
 

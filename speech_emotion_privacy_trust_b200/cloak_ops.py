@@ -5,23 +5,17 @@ import torch
 
 from . import _lib
 
-_WORKSPACES: dict[tuple[int, int, int], torch.Tensor] = {}
-
-
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _workspace(device: torch.device, wf: int) -> torch.Tensor:
-    """Partial-sum buffer + counters of the backward kernel, one per (device, W*F, stream): launches on different
-    streams must not share it."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), wf, _stream(device))
-    ws = _WORKSPACES.get(key)
-    if ws is None:
-        nbytes = _lib.lib().sept_cloak_bwd_workspace_bytes(wf)
-        ws = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device)   # counters start at zero, kernel re-zeroes
-        _WORKSPACES[key] = ws
-    return ws
+def new_workspace(device: torch.device, wf: int) -> torch.Tensor:
+    """Partial-sum buffer + column counters of the backward kernel (counters start at zero; the kernel leaves them at
+    zero again).  The OWNER decides its lifetime: a cloak_noise layer keeps one for as long as it lives -- allocated on
+    its first forward, i.e. before any CUDA-graph capture of the step, never inside one -- and callers of the functional
+    API get a fresh one per call.  Backward launches that may overlap (different streams) need different workspaces."""
+    nbytes = _lib.lib().sept_cloak_bwd_workspace_bytes(wf)
+    return torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device)
 
 
 def _ptr(t):
@@ -74,7 +68,8 @@ class CloakNoiseFunction(torch.autograd.Function):
     the separate -lambda*g launch and autograd's gradient accumulation pass."""
 
     @staticmethod
-    def forward(ctx, x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, twin, grl_lambda, draw=None):
+    def forward(ctx, x, locs, rhos, mask, eps, seed, offset, eps_std, min_scale, max_scale, twin, grl_lambda, draw=None,
+                workspace=None):
         _lib.require_cuda(x)
         x = _f32c(x)
         locs_c, rhos_c = _f32c(locs.detach()), _f32c(rhos.detach())
@@ -84,6 +79,7 @@ class CloakNoiseFunction(torch.autograd.Function):
                                              draw=draw)
         ctx.save_for_backward(eps_used, rhos_c, mask_c)
         ctx.cfg = (float(min_scale), float(max_scale), float(grl_lambda), bool(twin), tuple(locs.shape))
+        ctx.workspace = workspace
         if twin:
             return out, _alias(out)
         return out
@@ -93,7 +89,7 @@ class CloakNoiseFunction(torch.autograd.Function):
         eps_used, rhos_c, mask_c = ctx.saved_tensors
         min_scale, max_scale, lam, twin, pshape = ctx.cfg
         if g_a is None and g_b is None:
-            return (None,) * 13
+            return (None,) * 14
         if g_a is None:
             g_a = torch.zeros_like(g_b)
         g_a = _f32c(g_a)
@@ -105,13 +101,13 @@ class CloakNoiseFunction(torch.autograd.Function):
         dlocs = torch.empty(wf, dtype=torch.float32, device=dev)
         drhos = torch.empty(wf, dtype=torch.float32, device=dev) if need_rhos else None
         dx = torch.empty_like(g_a) if need_x else None
-        ws = _workspace(dev, wf)
+        ws = ctx.workspace if ctx.workspace is not None else new_workspace(dev, wf)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().sept_cloak_grl_bwd_f32(
                 g_a.data_ptr(), _ptr(g_b), lam, eps_used.data_ptr(), rhos_c.data_ptr(), _ptr(mask_c), min_scale, max_scale,
                 batch, wf, ws.data_ptr(), dlocs.data_ptr(), _ptr(drhos), _ptr(dx), _stream(dev)))
         return (dx, dlocs.view(pshape) if need_locs else None, drhos.view(pshape) if need_rhos else None,
-                None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 class GradientReversalFunction(torch.autograd.Function):

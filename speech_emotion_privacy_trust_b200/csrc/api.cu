@@ -164,7 +164,13 @@ int check_extract_shape(int n_fft, int hop, int n_mels, int n_mel_entries) {
 
 extern "C" {
 
-int sept_version(void) { return 100; }
+int sept_version(void) { return 200; }
+
+#ifndef SEPT_SRC_HASH
+#define SEPT_SRC_HASH "unknown"
+#endif
+/* the marker lets the loader read the hash out of the file without dlopen-ing a stale library */
+const char* sept_source_hash(void) { return "SEPT_SRC_HASH=" SEPT_SRC_HASH; }
 
 const char* sept_last_error(void) { return g_err.c_str(); }
 

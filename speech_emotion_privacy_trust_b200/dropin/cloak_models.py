@@ -25,6 +25,10 @@ class cloak_noise(nn.Module):
         self.rhos = nn.Parameter(torch.full(size, -2.0), requires_grad=True)          # ones - 3 (:33)
         self.device = device
         self.normal = torch.distributions.normal.Normal(0, EPS_STD)
+        # the reference's drivers pass CUDA scalars here (torch.tensor(0.01).to(device), training_cloak_with_grl.py:334);
+        # the kernels take plain floats: convert ONCE (a float() per forward would be a device sync, illegal in capture)
+        self._scale_bounds = (float(min_scale), float(max_scale))
+        self._workspace = None        # backward partial sums, owned by the layer (allocated on the first forward)
         self.external_eps = None      # set to a (1, W, F) tensor to supply eps instead of drawing it on the device
         self._draws = None            # device counter of samples drawn: the Philox offset lives on the GPU, so a captured
                                       # CUDA graph draws a fresh eps per replay; identical on every data-parallel rank
@@ -44,11 +48,23 @@ class cloak_noise(nn.Module):
             self._draws = torch.zeros(1, dtype=torch.int64, device=self.rhos.device)
         return None, torch.initial_seed(), self._draws
 
+    def _bounds(self):
+        lo, hi = self._scale_bounds
+        if not torch.is_tensor(self.min_scale) and not torch.is_tensor(self.max_scale):
+            lo, hi = float(self.min_scale), float(self.max_scale)       # plain numbers: follow later reassignment for free
+        return lo, hi
+
+    def _ws(self):
+        if self._workspace is None or self._workspace.device != self.rhos.device:
+            self._workspace = cloak_ops.new_workspace(self.rhos.device, self.rhos.numel())
+        return self._workspace
+
     def sample_noise(self, mask=None):
         eps, seed, draw = self._eps_source()
         if eps is None:
+            lo, hi = self._bounds()
             _, eps, _ = cloak_ops.cloak_forward_raw(None, self.locs.detach(), self.rhos.detach(), None, None, seed, 0,
-                                                    EPS_STD, self.min_scale, self.max_scale, draw=draw)
+                                                    EPS_STD, lo, hi, draw=draw)
             eps = eps.view(self.rhos.shape)
         eps = eps.to(self.rhos.device)
         if mask is not None:
@@ -57,14 +73,16 @@ class cloak_noise(nn.Module):
 
     def forward(self, input, mask=None):
         eps, seed, draw = self._eps_source()
-        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, 0, EPS_STD,
-                                                  self.min_scale, self.max_scale, False, 0.0, draw)
+        lo, hi = self._bounds()
+        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, 0, EPS_STD, lo, hi, False, 0.0,
+                                                  draw, self._ws())
 
     def forward_with_reversed_twin(self, input, mask, grl_lambda):
         """(y, y_rev): y_rev carries the same values and reverses its gradient by -grl_lambda inside the fused backward."""
         eps, seed, draw = self._eps_source()
-        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, 0, EPS_STD,
-                                                  self.min_scale, self.max_scale, True, float(grl_lambda), draw)
+        lo, hi = self._bounds()
+        return cloak_ops.CloakNoiseFunction.apply(input, self.locs, self.rhos, mask, eps, seed, 0, EPS_STD, lo, hi, True,
+                                                  float(grl_lambda), draw, self._ws())
 
 
 def _freeze(model):

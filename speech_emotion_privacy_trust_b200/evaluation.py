@@ -20,7 +20,7 @@ from .extraction import Layout
 EPS_STD = 0.1
 
 
-def suppression_mask(noise_layer, ratio: float, keep_above: bool = False) -> torch.Tensor | None:
+def suppression_mask(noise_layer, ratio: float) -> torch.Tensor | None:
     """Binary mask over (1, W, F): 0 where sigma exceeds the `ratio`-th percentile, 1 elsewhere
     (adversary_cloak_evaluation.py:263-267; np.nanpercentile's linear interpolation == torch.quantile).  The training
     script uses the (100 - ratio)-th percentile instead (training_cloak_with_grl.py:407-408): pass 100 - ratio."""
@@ -45,7 +45,11 @@ def cloak_evaluate(noise_layer, baseline_model, adversary_model, feat: torch.Ten
     argmax / mean over the utterance's windows of softmax(baseline(noisy)), softmax(adversary(noisy)).
 
     feat/lay/stats: frame-major log-mel, its layout and the speaker statistics (normalisation happens in the gather).
-    external_eps: optional (n_windows, W, F) noise samples, one per window in window-table order (parity tests)."""
+    external_eps: optional (n_windows, W, F) noise samples, one per window in window-table order (parity tests).
+    Without it the layer's own eps source is honoured: a patched `normal.sample` (the reference's draw site) is called
+    once per window, in window order, exactly like the reference's loop; `layer.external_eps` -- ONE (1, W, F) sample --
+    would give every window the same noise, which the reference never does, so it is rejected; otherwise eps comes from
+    the device Philox stream (one draw per window, counter advanced by the number of windows)."""
     baseline_model.eval()
     adversary_model.eval()
     dev = feat.device
@@ -57,6 +61,11 @@ def cloak_evaluate(noise_layer, baseline_model, adversary_model, feat: torch.Ten
     counts = torch.from_numpy(np.maximum(np.bincount(seg_host, minlength=n_utt), 1)).to(dev).unsqueeze(1).float()
     locs, rhos = noise_layer.locs.detach().float().contiguous(), noise_layer.rhos.detach().float().contiguous()
     mask_c = None if mask is None else mask.detach().to(dev).float().contiguous()
+    lo, hi = noise_layer._bounds() if hasattr(noise_layer, "_bounds") else (float(noise_layer.min_scale), float(noise_layer.max_scale))
+    if external_eps is None and getattr(noise_layer, "external_eps", None) is not None:
+        raise ValueError("cloak_evaluate draws one eps per window; layer.external_eps holds a single sample -- pass "
+                         "external_eps=(n_windows, W, F) instead")
+    sampler = vars(noise_layer.normal).get("sample") if external_eps is None and hasattr(noise_layer, "normal") else None
     emo_sum = gen_sum = None
     for a in range(0, n_win, max_windows):
         b = min(n_win, a + max_windows)
@@ -65,10 +74,11 @@ def cloak_evaluate(noise_layer, baseline_model, adversary_model, feat: torch.Ten
         seed, draw = 0, None
         if external_eps is not None:
             eps = external_eps[a:b].to(dev).float().contiguous().reshape(-1)
+        elif sampler is not None:
+            eps = torch.cat([sampler(noise_layer.rhos.shape).reshape(1, -1) for _ in range(b - a)]).to(dev).float().contiguous().reshape(-1)
         else:
             _, seed, draw = noise_layer._eps_source()
-        noisy, _, _ = cloak_ops.cloak_forward_raw(x, locs, rhos, mask_c, eps, seed, 0, EPS_STD, noise_layer.min_scale,
-                                                  noise_layer.max_scale, draw=draw, per_sample=True)
+        noisy, _, _ = cloak_ops.cloak_forward_raw(x, locs, rhos, mask_c, eps, seed, 0, EPS_STD, lo, hi, draw=draw, per_sample=True)
         p_emo = torch.softmax(baseline_model(noisy), dim=1)
         p_gen = torch.softmax(adversary_model(noisy), dim=1)
         if emo_sum is None:

@@ -142,7 +142,8 @@ def split_band_major(flat: torch.Tensor, lay: Layout, rows: int) -> list[torch.T
 
 # ---- host-buffer entry point: copies pipelined against the kernel ----------------------------------------------
 def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 800, n_mels: int = 128, hop: int = HOP_MEL,
-                out_host: torch.Tensor | None = None, device="cuda", chunk_samples: int = 1 << 24, n_streams: int = 3):
+                out_host: torch.Tensor | None = None, device="cuda", chunk_samples: int = 1 << 24, n_streams: int = 3,
+                sync: bool = True):
     """log-mel dB for a ragged batch that lives in HOST memory, result back in host memory (frame-major).
 
     wav_host may also be 16-bit PCM (int16): it is converted on the device as x / 32768, exactly what torchaudio.load does
@@ -150,7 +151,9 @@ def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 8
     The batch is cut into chunks of about `chunk_samples` samples at utterance boundaries; each chunk is copied to the
     device, extracted and copied back on one of `n_streams` streams, so the H2D copy, the kernel and the D2H copy of
     neighbouring chunks overlap (PCIe is full duplex).  Pass pinned tensors to get asynchronous copies.
-    Returns (out_host, frame_off_host)."""
+    Returns (out_host, frame_off_host).  With sync=True (default) the call returns once the last device->host copy has
+    landed, so out_host can be read straight away; sync=False returns as soon as the work is queued (the caller's current
+    stream is ordered after it: synchronise that stream, or the device, before touching out_host)."""
     dev = torch.device(device)
     if wav_host.is_cuda or wav_host.dtype not in (torch.float32, torch.int16) or wav_host.dim() != 1:
         raise ValueError("wav_host must be a 1-D float32 (or 16-bit PCM int16) host tensor")
@@ -220,4 +223,8 @@ def logmel_host(wav_host: torch.Tensor, utt_off_host: np.ndarray, n_fft: int = 8
             obuf.record_stream(main)
         for pbuf in pcm_bufs or []:
             pbuf.record_stream(main)
+        if sync:
+            done = torch.cuda.Event()
+            done.record(main)
+            done.synchronize()
     return out_host, frame_off

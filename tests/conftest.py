@@ -33,3 +33,5 @@ def golden_cloak():
 @pytest.fixture(scope="session")
 def golden_norm():
     return np.load(GOLDEN / "norm.npz")
+
+collect_ignore = ["ref_fixture"]          # verbatim reference sources (test fixtures), nothing to collect

@@ -76,9 +76,13 @@ def test_mfcc_golden(ex, gold_batch, golden_extraction):
         ref = golden_extraction[f"mfcc_{i}"][0]
         got = blocks[i].cpu().numpy()
         assert got.shape == ref.shape
-        if i in SPEECH or i == 5:
-            rel = np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-12)
-            assert rel < TOL_MFCC_REL, (i, rel)
+        # every golden utterance, including the pure tone (6): its mel bins 60-90 dB below the peak are rounding noise, but
+        # top_db clamps everything under max - 80 dB and the DCT averages the rest -- the reference itself is 1.2e-6 from
+        # fp64-exact arithmetic there, so the north_star tolerance applies unchanged
+        rel = np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-12)
+        assert rel < TOL_MFCC_REL, (i, rel)
+        exact = restate.mfcc(waves[i][None], dtype=np.float64)[0]
+        assert np.max(np.abs(got - exact)) / max(np.max(np.abs(exact)), 1e-12) < TOL_MFCC_REL, i
 
 
 def test_logmel_random_ragged_batch_vs_oracle(ex):
@@ -158,7 +162,7 @@ def test_corpus_scale_properties(ex):
     u = 311
     ref = restate.mel_spectrogram(wav[off[u]:off[u + 1]][None], 800, 128, dtype=np.float64)[0]
     e_strong, e_all = logmel_error(a[fo[u]:fo[u + 1]].cpu().numpy().T, ref)
-    assert e_strong < TOL_DB and e_all < TOL_DB_FLOOR
+    assert e_all < TOL_DB, e_all                                  # corpus-shaped audio: EVERY bin within 1e-3 dB of exact
     # MFCC on the same batch: finite, and the c0 row dominates like an energy term should
     m, mlay = ex.mfcc(batch)
     assert bool(torch.isfinite(m).all())
@@ -193,6 +197,28 @@ def test_other_hops_and_mel_counts_fuzz(ex):
         ex.logmel(ex.RaggedAudio.from_list([np.zeros(4000, np.float32)]), n_fft=800, hop=161)
 
 
+def test_mfcc_fuzz_vs_oracle(ex):
+    """MFCC at the one configuration the C ABI accepts (n_fft 400, hop 200, 128 mels, 40 coefficients, three streams), on
+    ragged batches that exercise what is special about it: the per-utterance top_db floor (loud + near-silent halves in
+    one utterance, whole utterances at the 1e-10 clamp), frame-count boundaries, the shortest legal utterance."""
+    from speech_emotion_privacy_trust_b200 import synth
+    rng = np.random.default_rng(404)
+    lens = [201, 399, 400, 401, 999, 1000, 1001, 1599, 1600] + [int(rng.integers(202, 40000)) for _ in range(15)]
+    waves = [synth.speech_shaped(n, rng) for n in lens]
+    waves[9][: len(waves[9]) // 2] *= 1e-4                         # half the utterance 80 dB down: sits on the top_db floor
+    waves[10] *= 1e-6                                              # every band at the 1e-10 power clamp (-100 dB)
+    waves[11][len(waves[11]) // 3:] = 0.0                          # digital silence after speech
+    waves.append(np.zeros(777, np.float32))
+    batch = ex.RaggedAudio.from_list(waves)
+    flat, lay = ex.mfcc(batch)
+    blocks = ex.split_band_major(flat, lay, 120)
+    for u, w in enumerate(waves):
+        ref = restate.mfcc(w[None], dtype=np.float64)[0]
+        got = blocks[u].cpu().numpy()
+        assert got.shape == ref.shape == (120, 1 + len(w) // 200), u
+        assert np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-12) < TOL_MFCC_REL, (u, len(w))
+
+
 def test_against_reference_port_at_corpus_lengths(ex):
     """2-10 s utterances (the corpus shape of BASELINE.json configs[0]) against oracle/ref_port.py -- the reference's own
     callables restated on torchaudio, bit-identical to the reference on the golden vectors -- run on the host CPU."""
@@ -207,12 +233,14 @@ def test_against_reference_port_at_corpus_lengths(ex):
     b1, b2, bm = ex.split_band_major(m1, lay, 128), ex.split_band_major(m2, lay, 128), ex.split_band_major(mf, mlay, 120)
     for u in range(12):
         a = torch.from_numpy(wav[off[u]:off[u + 1]])[None]
-        for got, ref in ((b1[u], ref_port.mel_spectrogram(a, 800, 128)[0]), (b2[u], ref_port.mel_spectrogram(a, 1600, 128)[0])):
+        for got, ref, n_fft in ((b1[u], ref_port.mel_spectrogram(a, 800, 128)[0], 800), (b2[u], ref_port.mel_spectrogram(a, 1600, 128)[0], 1600)):
             got, ref = got.cpu().numpy(), ref.numpy()
             assert got.shape == ref.shape
-            strong = ref > ref.max(axis=0, keepdims=True) - 50.0
-            assert np.max(np.abs(got - ref)[strong]) < TOL_DB          # both sides fp32: compare where the signal is
-            assert np.max(np.abs(got - ref)) < 2 * TOL_DB_FLOOR
+            # corpus-shaped audio has no bin more than 50 dB below its frame's peak: ALL bins within north_star's 1e-3 dB
+            # of the reference's own fp32 output, and of fp64-exact arithmetic
+            assert np.max(np.abs(got - ref)) < TOL_DB, (u, n_fft, float(np.max(np.abs(got - ref))))
+            exact = restate.mel_spectrogram(a.numpy(), n_fft, 128, dtype=np.float64)[0]
+            assert np.max(np.abs(got - exact)) < TOL_DB, (u, n_fft, float(np.max(np.abs(got - exact))))
         ref = ref_port.mfcc(a)[0]
         got = bm[u].cpu().numpy()
         assert got.shape == ref.shape
@@ -228,7 +256,11 @@ def test_host_buffer_api_float_and_pcm16(ex):
     wav_q = pcm.astype(np.float32) / 32768.0                      # what torchaudio.load(normalize=True) returns
     ref, lay = ex.logmel(ex.RaggedAudio(torch.from_numpy(wav_q).cuda(), off), n_fft=800)
     for host, tag in ((torch.from_numpy(wav_q).pin_memory(), "float32"), (torch.from_numpy(pcm).pin_memory(), "pcm16")):
-        out, fo = ex.logmel_host(host, off, n_fft=800, chunk_samples=1 << 18, n_streams=3)     # 5+ chunks
-        torch.cuda.synchronize()
+        ref_host = ref.cpu()
+        out = torch.full((lay.total_frames, 128), float("nan")).pin_memory()
+        out, fo = ex.logmel_host(host, off, n_fft=800, out_host=out, chunk_samples=1 << 18, n_streams=3)     # 5+ chunks
+        assert torch.equal(out, ref_host), tag                    # read right after the call: no external synchronize
         assert np.array_equal(fo, lay.frame_off_host), tag
-        assert torch.equal(out, ref.cpu()), tag
+        out2, _ = ex.logmel_host(host, off, n_fft=800, chunk_samples=1 << 18, n_streams=3, sync=False)
+        torch.cuda.current_stream().synchronize()                 # the async contract: the current stream is ordered after it
+        assert torch.equal(out2, ref_host), tag

@@ -27,6 +27,29 @@ def test_library_exports_every_declared_symbol():
     assert [handle.sept_frames_per_item(n) for n in (400, 800, 1600, 1024)] == [8, 4, 2, 0]
 
 
+def test_loader_refuses_a_stale_library(tmp_path, monkeypatch):
+    """a prebuilt .so compiled from other sources than the tree holds must never be tested silently.  The
+    library carries the sha256 of its sources; the loader compares it with the tree and rebuilds or raises."""
+    from speech_emotion_privacy_trust_b200 import _lib, build
+    assert build.built_hash() == build.source_hash() and not build.stale()
+    assert _lib.lib().sept_source_hash().decode() == "SEPT_SRC_HASH=" + build.source_hash()
+    # a copy whose embedded hash is wrong + no compiler: loading must raise, not fall through
+    fake = tmp_path / "libsept_b200.so"
+    blob = build.LIB.read_bytes().replace(build.source_hash().encode(), b"0" * 64)
+    fake.write_bytes(blob)
+    monkeypatch.setattr(build, "LIB", fake)
+    monkeypatch.setattr(build, "_nvcc", lambda: (_ for _ in ()).throw(RuntimeError("nvcc not found")))
+    monkeypatch.setattr(_lib, "_LIB", None)
+    assert build.stale()
+    with pytest.raises(RuntimeError, match="stale"):
+        _lib.lib()
+    # the mtime of the sources plays no role (the tree is copied to the GPU box): touching a file is not "stale"
+    monkeypatch.undo()
+    src = CSRC / "philox.cuh"
+    src.touch()
+    assert not build.stale()
+
+
 def test_layout_helper_matches_reference_frame_rule():
     from speech_emotion_privacy_trust_b200 import _lib
     lens = np.array([801, 1600, 4000, 7777, 16000, 48001], dtype=np.int64)

@@ -1,0 +1,159 @@
+"""Model-level pins: the drop-in classifiers and cloak wrappers, and oracle/train_port.py,
+against tests/golden/models.npz -- outputs of the REAL reference classes (oracle/make_golden_models.py; weights and
+inputs are rebuilt from (seed, parameter name) by oracle/weights.py).  Covers att in {None,'self_att'}, pooling in
+{None,'mean'}, mask, global_feature, eval and train mode, and the combinations on which the reference raises."""
+import json
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import make_golden_models as G
+from oracle import weights as W
+
+META = json.loads((GOLDEN / "models.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN / "models.npz")
+
+
+@pytest.fixture(scope="module")
+def dropins():
+    from speech_emotion_privacy_trust_b200 import dropin
+    dropin.install()
+    for m in ("baseline_models", "cloak_models", "reversal_gradient"):
+        sys.modules.pop(m, None)
+    import baseline_models
+    import cloak_models
+    assert baseline_models.__file__.startswith(dropin.HERE) and cloak_models.__file__.startswith(dropin.HERE)
+    return baseline_models, cloak_models
+
+
+def _parse(name):
+    parts = name.split("|")
+    return [None if p == "None" else (int(p) if p.isdigit() else p) for p in parts]
+
+
+def _close(got, want, rel, name):
+    scale = max(float(np.abs(want).max()), 1e-6)
+    err = float(np.abs(np.asarray(got, np.float64) - want).max())
+    assert err <= rel * scale, f"{name}: {err:.3e} > {rel:g} * {scale:.3e}"
+
+
+# ---- a12: plain classifiers (stock PyTorch compute -> runs on the CPU too) ------------------------------------------
+@pytest.mark.parametrize("name", META["classifiers"])
+def test_dropin_classifier_forward_equals_reference(golden, dropins, name):
+    _, cls, att, pred, glob = _parse(name)
+    torch.set_num_threads(1)
+    m = G.build_classifier(dropins[0], cls, att, pred, glob)
+    W.fill_state(m, META["seed"])
+    m.eval()
+    x, _, _, g, _, _ = (torch.from_numpy(a) for a in W.case_inputs(META["seed"]))
+    with torch.no_grad():
+        res = m(x, global_feature=g) if glob else m(x)
+    res = res if isinstance(res, tuple) else (res,)
+    for i, r in enumerate(res):
+        _close(r.numpy(), golden[f"{name}#out{i}"], 1e-5, name)
+
+
+@pytest.mark.parametrize("name", [n for n in META["raises"] if n.startswith("clf")])
+def test_dropin_classifier_raises_where_the_reference_raises(dropins, name):
+    _, cls, att, pred, glob = _parse(name)
+    m = G.build_classifier(dropins[0], cls, att, pred, glob).eval()
+    x, _, _, g, _, _ = (torch.from_numpy(a) for a in W.case_inputs(META["seed"]))
+    with pytest.raises(RuntimeError), torch.no_grad():
+        m(x, global_feature=g) if glob else m(x)
+
+
+# ---- oracle/train_port.py pinned to the reference -------------------------------------------------------------------
+def test_train_port_equals_reference_golden(golden):
+    from oracle import train_port
+    torch.set_num_threads(1)
+    name = "grl|two_d_cnn_lstm|None|mean|0|0"
+    noise = train_port.CloakNoise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 10.0, "cpu")
+    model = train_port.CloakGRLModel(train_port.Classifier("emotion"), train_port.Classifier("gender"), noise, 0.1)
+    W.fill_state(model, META["seed"])            # keyed by parameter name: the port's keys are a subset of the reference's
+    x, eps, _, _, g1, g2 = (torch.from_numpy(a) for a in W.case_inputs(META["seed"]))
+    model.intermed.normal.sample = lambda shape: eps.clone()
+    model.eval()
+    with torch.no_grad():
+        p1, p2, noisy = model(x)
+    _close(p1.numpy(), golden[f"{name}#eval_preds"], 1e-5, "eval preds")
+    _close(p2.numpy(), golden[f"{name}#eval_preds_grl"], 1e-5, "eval preds_grl")
+    _close(noisy[:, 0][G.SUB].numpy(), golden[f"{name}#noisy_sub"], 1e-6, "noisy")
+    model.train()
+    W.dropout_off(model)
+    p1, p2, _ = model(x)
+    ((p1 * g1).sum() + (p2 * g2).sum()).backward()
+    _close(p1.detach().numpy(), golden[f"{name}#train_preds"], 1e-5, "train preds")
+    _close(model.intermed.locs.grad[G.SUB].numpy(), golden[f"{name}#dlocs_sub"], 1e-4, "dlocs")
+    _close(model.intermed.rhos.grad[G.SUB].numpy(), golden[f"{name}#drhos_sub"], 1e-4, "drhos")
+    _close(model.gender_model.conv[1][0].weight.grad.numpy(), golden[f"{name}#gender_conv0_wgrad"], 1e-4, "conv0 wgrad")
+
+
+def test_train_port_is_bit_identical_to_the_reference_classes():
+    """Same machine, same thread count, same kernels: the restated step equals the vendored reference classes exactly
+    (forward, loss of training_cloak_with_grl.py:141-160, every gradient)."""
+    import ref_harness as H
+    from oracle import train_port
+    torch.set_num_threads(1)
+    ref = H.load_driver("training_cloak_with_grl", "reference")
+    ref_model = H.build_grl_model(ref, "cpu")
+    noise = train_port.CloakNoise(torch.zeros(1, 200, 128), torch.ones(1, 200, 128), 0.01, 10.0, "cpu")
+    port = train_port.CloakGRLModel(train_port.Classifier("emotion"), train_port.Classifier("gender"), noise, 0.1)
+    for m in (ref_model, port):
+        W.fill_state(m, 7)
+        m.train()
+        W.dropout_off(m)
+    x, eps, mask, _, _, _ = (torch.from_numpy(a) for a in W.case_inputs(7, batch=4))
+    emo, gen = torch.tensor([0, 3, 1, 2]), torch.tensor([1, 0, 0, 1])
+    w = torch.tensor([1.0, 2.5, 0.7, 1.3])
+    outs = []
+    for m, is_ref in ((ref_model, True), (port, False)):
+        m.intermed.normal.sample = lambda shape: eps.clone()
+        p1, p2, noisy = m(x.double(), mask=mask, grl=False, pooling="mean") if is_ref else m(x.double(), mask)
+        loss = train_port.reference_loss(m, p1, p2, emo, gen, w, 0.1, 0.05)
+        loss.backward()
+        outs.append((p1.detach(), p2.detach(), noisy, loss.detach(), m.intermed.locs.grad, m.intermed.rhos.grad,
+                     m.gender_model.conv[1][0].weight.grad, m.gender_model.rnn.weight_ih_l0.grad))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+# ---- a9 / a10: cloak wrappers on the GPU ----------------------------------------------------------------------------
+@pytest.fixture()
+def fp32_math():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", META["wrappers"])
+def test_dropin_cloak_wrapper_equals_reference(golden, dropins, fp32_math, name):
+    wrapper, cls, att, pooling, use_mask, glob = _parse(name)
+    model = G.build_wrapper(dropins[0], dropins[1], wrapper, cls, att, glob, device="cuda")
+    out = G.run_wrapper(model, wrapper, pooling, bool(use_mask), glob, device="cuda")
+    _close(out["noisy_sub"], golden[f"{name}#noisy_sub"], 1e-6, "noisy")                # cloak forward: 1e-6 (north_star)
+    for k in ("eval_preds", "eval_preds_grl", "train_preds", "train_preds_grl"):
+        if k in out:
+            _close(out[k], golden[f"{name}#{k}"], 2e-4, k)
+    for k in ("dlocs_sub", "drhos_sub", "gender_conv0_wgrad", "gender_head_wgrad"):
+        if k in out:
+            _close(out[k], golden[f"{name}#{k}"], 2e-3, k)
+    assert abs(float(out["dlocs_sum"]) - float(golden[f"{name}#dlocs_sum"])) <= 2e-3 * max(1.0, float(golden[f"{name}#drhos_abs_sum"]))
+    assert all(p.grad is None for p in model.original_model.parameters())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in META["raises"] if not n.startswith("clf")])
+def test_dropin_cloak_wrapper_raises_where_the_reference_raises(dropins, name):
+    wrapper, cls, att, pooling, use_mask, glob = _parse(name)
+    model = G.build_wrapper(dropins[0], dropins[1], wrapper, cls, att, glob, device="cuda")
+    with pytest.raises(RuntimeError):
+        G.run_wrapper(model, wrapper, pooling, bool(use_mask), glob, device="cuda")

@@ -1,0 +1,215 @@
+"""north_star: "training_cloak*.py and adversary_cloak_evaluation.py run unchanged".  The reference's own train() / test()
+functions (verbatim copies under tests/ref_fixture/, driven by tests/ref_harness.py) run on the GPU twice -- with the
+reference's model classes and with the drop-ins -- from the same checkpoint, the same batches and the same eps tape
+(injected at the reference's own draw site, noise_model.normal.sample).  Asserted: per-step prediction trajectory and
+epoch losses (1e-4), final mu / rho / adversary weights, and emotion UAR / accuracy + adversary gender accuracy from the
+reference's ReturnResultDict within the run-to-run noise measured between two reference runs with different eps seeds.
+Matches training_cloak_with_grl.py:43-194, training_cloak.py:45-184, adversary_cloak_evaluation.py:40-110."""
+import copy
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import ref_harness as H
+
+pytestmark = pytest.mark.gpu
+REPORT = {}
+
+
+@pytest.fixture(scope="module")
+def world():
+    dev = torch.device("cuda:0")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True                       # what the reference's setup_seed() sets (:74)
+    tr, va = H.synthetic_split(96, 1), H.synthetic_split(24, 2)
+    te = H.synthetic_split(24, 3, frames=(200, 420))
+    base = H.load_driver("training_adversary_baselines", "reference")
+    torch.manual_seed(8)
+    res_e, emo2d = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", epochs=6)
+    res_d, emodeep = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", model_type="deep-2d-cnn-lstm", epochs=6)
+    res_g, adv = H.run_baseline_training(base, dev, tr, va, te, pred="gender", epochs=3)
+    # adversary_cloak_evaluation.py calls the cloak model without `pooling` (:79): only att='self_att' classifiers run (Appendix B)
+    res_ea, emo_att = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", att="self_att", epochs=6)
+    res_ga, adv_att = H.run_baseline_training(base, dev, tr, va, te, pred="gender", att="self_att", epochs=3)
+    REPORT["pretrained"] = {"emotion_2d_test_uar": res_e[-1]["test"]["combine"]["rec"]["emotion"],
+                            "emotion_deep_test_uar": res_d[-1]["test"]["combine"]["rec"]["emotion"],
+                            "adversary_test_acc": res_g[-1]["test"]["combine"]["acc"]["gender"]}
+    yield {"dev": dev, "train": tr, "valid": va, "test": te, "emo2d": emo2d, "emodeep": emodeep, "adv": adv,
+           "emo_att": emo_att, "adv_att": adv_att}
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = tf32
+    print("\nREF_CALLER_PARITY " + json.dumps(REPORT))
+    try:
+        (H.REPO / "gpurun_out").mkdir(exist_ok=True)
+        (H.REPO / "gpurun_out" / "ref_caller_parity.json").write_text(json.dumps(REPORT, indent=1))
+    except OSError:
+        pass
+
+
+def _scores(results, pred="emotion"):
+    out = {}
+    for split in ("train", "validate", "test"):
+        r = results[-1][split]["combine"]
+        out[split] = {"acc": float(r["acc"][pred]), "uar": float(r["rec"][pred])}
+        if split != "test":
+            out[split]["loss"] = float(r["loss"][pred])
+    return out
+
+
+def _worst(a, b):
+    return max(abs(a[s][k] - b[s][k]) for s in a for k in ("acc", "uar"))
+
+
+def test_grl_train_and_test_parity(world):
+    dev, tr, va, te = world["dev"], world["train"], world["valid"], world["test"]
+    ref = H.load_driver("training_cloak_with_grl", "reference")
+    new = H.load_driver("training_cloak_with_grl", "dropin")
+    torch.manual_seed(8)
+    seed_model = H.build_grl_model(ref, dev)
+    seed_model.original_model.load_state_dict(world["emo2d"].state_dict())         # the `model.pt` load of :395
+    state = copy.deepcopy(seed_model.state_dict())
+    H.build_grl_model(new, dev, state)                                             # strict load into the drop-in: same keys
+
+    runs = {}
+    for tag, mod, eps_seed in (("ref_a", ref, 5), ("ref_b", ref, 6), ("new", new, 5), ("new_philox", new, None)):
+        rec = []
+        torch.manual_seed(8)
+        res, model, tape = H.run_grl_training(mod, dev, tr, va, te, state=state, epochs=2, batch_size=8, eps_seed=eps_seed, record=rec)
+        runs[tag] = {"res": res, "model": model, "rec": rec, "scores": _scores(res), "draws": None if tape is None else tape.draws}
+    a, b, n, free = runs["ref_a"], runs["ref_b"], runs["new"], runs["new_philox"]
+    assert a["draws"] == n["draws"] and len(a["rec"]) == len(n["rec"]) == 2 * 12
+
+    traj = max(max(float(np.abs(pa[0] - pn[0]).max()), float(np.abs(pa[1] - pn[1]).max())) for pa, pn in zip(a["rec"], n["rec"]))
+    losses = max(abs(ra[s]["combine"]["loss"]["emotion"] - rn[s]["combine"]["loss"]["emotion"])
+                 for ra, rn in zip(a["res"], n["res"]) for s in ("train", "validate"))
+    dl = float((a["model"].intermed.locs - n["model"].intermed.locs).abs().max())
+    dr = float((a["model"].intermed.rhos - n["model"].intermed.rhos).abs().max())
+    wa, wn = a["model"].gender_model.state_dict(), n["model"].gender_model.state_dict()
+    dw = max(float((wa[k].float() - wn[k].float()).abs().max()) for k in wa)
+    moved = float((a["model"].intermed.locs - state["intermed.locs"]).abs().max())
+    noise = _worst(a["scores"], b["scores"])
+    one_sample = 1.0 / len(te)
+    REPORT["grl"] = {"steps": len(a["rec"]), "trajectory_max_abs_diff": traj, "epoch_loss_max_abs_diff": losses, "locs_diff": dl, "rhos_diff": dr,
+                     "gender_weights_diff": dw, "locs_moved_by_training": moved, "scores_ref_a": a["scores"], "scores_ref_b": b["scores"],
+                     "scores_dropin": n["scores"], "scores_dropin_philox": free["scores"], "run_to_run_noise": noise}
+    assert traj < 1e-4, traj                      # same eps, same batches: the logits of every training step agree
+    assert losses < 1e-4, losses
+    assert dl < 1e-5 and dr < 1e-5 and dw < 1e-4, (dl, dr, dw)
+    assert moved > 1e-4                            # ... and training did move the cloak parameters
+    assert _worst(a["scores"], n["scores"]) <= max(noise, one_sample) + 1e-9          # UAR / accuracy within run-to-run noise
+    # device Philox eps instead of the CPU tape (the production configuration): another noise realisation
+    assert _worst(a["scores"], free["scores"]) <= max(2 * noise, 3 * one_sample) + 1e-9
+    assert all(p.grad is None for p in n["model"].original_model.parameters())
+    world["grl_state"] = copy.deepcopy(n["model"].state_dict())
+
+
+def test_cloak_train_and_test_parity(world):
+    """training_cloak.py (two_d_cnn_lstm_syn over deep_two_d_cnn_lstm, pooling None)."""
+    dev, tr, va, te = world["dev"], world["train"], world["valid"], world["test"]
+    ref = H.load_driver("training_cloak", "reference")
+    new = H.load_driver("training_cloak", "dropin")
+    torch.manual_seed(8)
+    seed_model = H.build_syn_model(ref, dev)
+    seed_model.original_model.load_state_dict(world["emodeep"].state_dict())
+    state = copy.deepcopy(seed_model.state_dict())
+    out = {}
+    for tag, mod, eps_seed in (("ref_a", ref, 5), ("ref_b", ref, 6), ("new", new, 5)):
+        rec = []
+        torch.manual_seed(8)
+        res, model, tape = H.run_cloak_training(mod, dev, tr, va, te, state=state, epochs=2, batch_size=8, eps_seed=eps_seed, record=rec)
+        out[tag] = (res, model, rec, _scores(res))
+    traj = max(float(np.abs(pa - pn).max()) for pa, pn in zip(out["ref_a"][2], out["new"][2]))
+    dl = float((out["ref_a"][1].intermed.locs - out["new"][1].intermed.locs).abs().max())
+    dr = float((out["ref_a"][1].intermed.rhos - out["new"][1].intermed.rhos).abs().max())
+    noise = _worst(out["ref_a"][3], out["ref_b"][3])
+    REPORT["cloak"] = {"steps": len(out["new"][2]), "trajectory_max_abs_diff": traj, "locs_diff": dl, "rhos_diff": dr,
+                       "scores_ref_a": out["ref_a"][3], "scores_dropin": out["new"][3], "run_to_run_noise": noise}
+    assert traj < 1e-4 and dl < 1e-5 and dr < 1e-5, (traj, dl, dr)
+    assert _worst(out["ref_a"][3], out["new"][3]) <= max(noise, 1.0 / len(te)) + 1e-9
+    world["syn_state"] = copy.deepcopy(out["new"][1].state_dict())
+
+
+def test_adversary_cloak_evaluation_parity(world):
+    """adversary_cloak_evaluation.test() with both model sets, and the batched device evaluator on the same eps."""
+    from speech_emotion_privacy_trust_b200 import evaluation, normalization as nz
+    from speech_emotion_privacy_trust_b200.extraction import Layout
+    dev, te = world["dev"], world["test"]
+    ref = H.load_driver("adversary_cloak_evaluation", "reference")
+    new = H.load_driver("adversary_cloak_evaluation", "dropin")
+    if "grl_state" not in world:
+        pytest.skip("needs the cloak parameters trained by test_grl_train_and_test_parity")
+    res = {}
+    for tag, mod in (("ref", ref), ("new", new)):
+        mk = lambda pred: mod.two_d_cnn_lstm(input_channel=1, input_spec_size=128, cnn_filter_size=64, pred=pred, lstm_hidden_size=64,
+                                             num_layers_lstm=2, attention_size=128, att="self_att", global_feature=0).to(dev)
+        base, adv = mk("emotion"), mk("gender")
+        base.load_state_dict(world["emo_att"].state_dict())
+        adv.load_state_dict(world["adv_att"].state_dict())
+        mus, scale = torch.zeros((1, 200, 128)).to(dev), torch.ones((1, 200, 128)).to(dev)
+        noise = mod.cloak_noise(mus, scale, torch.tensor(0.01).to(dev), torch.tensor(5).to(dev), dev).to(dev)     # max_scale 5 (:205)
+        cloak = mod.two_d_cnn_lstm_syn(base, noise).to(dev)                                                      # :243, grl 0
+        with torch.no_grad():
+            cloak.intermed.locs.copy_(world["grl_state"]["intermed.locs"])
+            cloak.intermed.rhos.copy_(world["grl_state"]["intermed.rhos"])
+        per_mask = {}
+        for ratio in (0, 40):
+            mask = None
+            if ratio:
+                thr = np.nanpercentile(cloak.intermed.scales().detach().cpu().numpy(), ratio)       # :266
+                sc = cloak.intermed.scales()
+                mask = torch.where(sc > thr, torch.zeros(sc.shape).to(dev), torch.ones(sc.shape).to(dev))
+            probs = {"emo": [], "adv": []}
+            h1 = base.register_forward_hook(lambda m, i, o: probs["emo"].append(torch.softmax(o, 1)[0].detach().cpu().numpy()))
+            h2 = adv.register_forward_hook(lambda m, i, o: probs["adv"].append(torch.softmax(o, 1)[0].detach().cpu().numpy()))
+            emo_r, adv_r, tape = H.run_adversary_evaluation(mod, dev, cloak, base, adv, te, mask=mask, eps_seed=9, grl=0)
+            h1.remove(), h2.remove()
+            per_mask[ratio] = {"emo": emo_r["combine"], "adv": adv_r["combine"], "probs": probs, "mask": mask, "draws": tape.draws}
+        res[tag] = {"cloak": cloak, "base": base, "adv": adv, "per_mask": per_mask}
+    for ratio in (0, 40):
+        r, n = res["ref"]["per_mask"][ratio], res["new"]["per_mask"][ratio]
+        assert r["draws"] == n["draws"]
+        for k in ("emo", "adv"):
+            d = max(float(np.abs(x - y).max()) for x, y in zip(r["probs"][k], n["probs"][k]))
+            assert d < 1e-4, (ratio, k, d)
+        assert r["emo"]["acc"]["emotion"] == n["emo"]["acc"]["emotion"] and r["emo"]["rec"]["emotion"] == n["emo"]["rec"]["emotion"]
+        assert r["adv"]["acc"]["gender"] == n["adv"]["acc"]["gender"] and r["adv"]["rec"]["gender"] == n["adv"]["rec"]["gender"]
+    REPORT["adversary_eval"] = {str(ratio): {"emotion_uar": float(res["new"]["per_mask"][ratio]["emo"]["rec"]["emotion"]),
+                                             "emotion_acc": float(res["new"]["per_mask"][ratio]["emo"]["acc"]["emotion"]),
+                                             "adversary_gender_acc": float(res["new"]["per_mask"][ratio]["adv"]["acc"]["gender"])} for ratio in (0, 40)}
+
+    # the batched device evaluator (evaluation.cloak_evaluate) against the reference's window loop, same eps per window
+    n = res["new"]
+    feats = [np.asarray(d["data"][0], np.float32) for d in te.values()]
+    fo = np.concatenate([[0], np.cumsum([f.shape[0] for f in feats])]).astype(np.int64)
+    lay = Layout(fo, torch.from_numpy(fo).to(dev), torch.zeros(len(fo), dtype=torch.int32, device=dev))
+    feat = torch.from_numpy(np.concatenate(feats)).to(dev)
+    stats = torch.zeros((1, 5, 128), device=dev)
+    stats[0, 2] = 1.0 - 1e-5                                    # identity z-norm: the test split is already normalised
+    st = nz.SpeakerStats(["all"], stats, torch.zeros(len(feats), dtype=torch.int32, device=dev))
+    n_win = sum((f.shape[0] - 200) // 50 + 1 for f in feats)
+    tape = H.EpsTape(9)
+    eps = torch.cat([tape((1, 200, 128)) for _ in range(n_win)]).to(dev)
+    for ratio in (0, 40):
+        pm = n["per_mask"][ratio]
+        e_pred, g_pred, e_prob, g_prob = evaluation.cloak_evaluate(n["cloak"].intermed, n["base"], n["adv"], feat, lay, st, mask=pm["mask"],
+                                                                   external_eps=eps)
+        w = 0
+        truth_e, truth_g = [], []
+        for u, (f, d) in enumerate(zip(feats, te.values())):
+            k = (f.shape[0] - 200) // 50 + 1
+            me = np.mean(np.array(pm["probs"]["emo"][w:w + k]), axis=0)
+            mg = np.mean(np.array(pm["probs"]["adv"][w:w + k]), axis=0)
+            w += k
+            assert np.max(np.abs(me - e_prob[u])) < 2e-4 and np.max(np.abs(mg - g_prob[u])) < 2e-4
+            assert int(np.argmax(me)) == int(e_pred[u]) and int(np.argmax(mg)) == int(g_pred[u])
+            truth_e.append(H.EMO.index(d["label"])), truth_g.append(H.GEN.index(d["gender"]))
+        if ratio == 0:                       # the layer's own draw site (patched normal.sample) is honoured window by window
+            n["cloak"].intermed.normal.sample = H.EpsTape(9)
+            again = evaluation.cloak_evaluate(n["cloak"].intermed, n["base"], n["adv"], feat, lay, st, mask=None)
+            assert np.array_equal(again[2], e_prob) and np.array_equal(again[3], g_prob)
+            assert n["cloak"].intermed.normal.sample.draws == n_win
+        from sklearn.metrics import accuracy_score, recall_score
+        assert recall_score(truth_e, e_pred, average="macro") == pytest.approx(float(pm["emo"]["rec"]["emotion"]))
+        assert accuracy_score(truth_g, g_pred) == pytest.approx(float(pm["adv"]["acc"]["gender"]))
