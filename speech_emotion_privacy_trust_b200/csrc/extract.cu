@@ -56,6 +56,14 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- optional per-phase cycle counters (diagnostic builds only: -DSEPT_PHASE_CLOCKS, tools/phase_clocks.py) ----------
+#ifdef SEPT_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define SEPT_TICK(i) do { const long long now_ = clock64(); if (lane == 0) atomicAdd(&g_phase_clk[i], (unsigned long long)(now_ - tick_last)); tick_last = now_; } while (0)
+#else
+#define SEPT_TICK(i) do { } while (0)
+#endif
+
 struct ItemRef {
     const float* wav;      // utterance start
     long long f0;          // first output frame of the utterance
@@ -347,6 +355,9 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     }
 
     constexpr int n_streams = (MODE == kModeMfccPower) ? 2 : 1;
+#ifdef SEPT_PHASE_CLOCKS
+    long long tick_last = clock64();
+#endif
     for (; item < end; item += kExtractWarps) {
 #pragma unroll 1
         for (int stream = 0; stream < n_streams; ++stream) {
@@ -362,6 +373,7 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
             };
             if (cur.interior) {
                 if (stream == 0) { cp_async_wait_all(); __syncwarp(); }
+                SEPT_TICK(0);
                 if (deriv) run_pass1(std::true_type{});
                 else run_pass1(std::false_type{});
             } else {
@@ -370,7 +382,9 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                 __syncwarp();
                 run_pass1(std::false_type{});
             }
+            SEPT_TICK(1);
             __syncwarp();                                        // stage is free, Y is complete
+            SEPT_TICK(2);
 
             ItemRef nxt = cur;
             if (stream == n_streams - 1 && item + kExtractWarps < end) {
@@ -378,6 +392,7 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                 if (nxt.interior) prefetch(nxt);                 // overlaps pass 2, split and mel of this item
             }
 
+            SEPT_TICK(3);
             if constexpr (R <= 16) {
                 // fused pass 2 + real split + power: rows j and 25-j stay in registers; the tile is overwritten by P only
                 // after every lane has loaded its rows
@@ -397,12 +412,15 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                         pass2_split<G>(p, j, Y, tw, pu[r], pv[r]);
                     }
                 }
+                SEPT_TICK(4);
                 __syncwarp();
+                SEPT_TICK(5);
 #pragma unroll
                 for (int r = 0; r < ROUNDS; ++r) {
                     int p, j;
                     if (G::ps_task(lane, r, p, j)) pass2_split_store<G>(p, j, P, pu[r], pv[r]);
                 }
+                SEPT_TICK(6);
             } else {
 #pragma unroll 1
                 for (int task = lane; task < G::P2_TASKS; task += 32) pass2_row<G>(task, Y);
@@ -423,6 +441,7 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                 split_store_all<G>(lane, P, a, b, on0);
             }
             __syncwarp();
+            SEPT_TICK(7);
 
             // ---- mel bands (lane = band, all frame pairs of the item) + log + store --------------------------
             {
@@ -430,7 +449,9 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
                 if constexpr (FAST) mel_fast<G, MODE>(lane, P, taddr, prm, job);
                 else mel_rounds<G, MODE>(lane, P, melp, n_mels, prm, job);
             }
+            SEPT_TICK(8);
             __syncwarp();                                        // P reads done before the next pass 1 overwrites Y
+            SEPT_TICK(9);
             if (stream == n_streams - 1) cur = nxt;
         }
     }
@@ -666,3 +687,13 @@ cudaError_t launch_mfcc_dct(const MfccDctParams& prm, cudaStream_t stream) {
 }
 
 }  // namespace sept
+
+#ifdef SEPT_PHASE_CLOCKS
+extern "C" int sept_debug_phase_clocks(unsigned long long* out_host, int reset) {
+    unsigned long long zero[16] = {0};
+    cudaDeviceSynchronize();
+    if (out_host && cudaMemcpyFromSymbol(out_host, sept::g_phase_clk, sizeof(zero)) != cudaSuccess) return -1;
+    if (reset && cudaMemcpyToSymbol(sept::g_phase_clk, zero, sizeof(zero)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif

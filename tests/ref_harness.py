@@ -76,9 +76,12 @@ def make_args(**over) -> Namespace:
     return Namespace(**base)
 
 
-def synthetic_split(n: int, seed: int, frames=(200, 200), shift: float = 0.5, n_speakers: int = 6, emo_shift: float = 1.0) -> dict:
+def synthetic_split(n: int, seed: int, frames=(200, 200), shift: float = 0.5, n_speakers: int = 6, emo_shift: float = 1.0,
+                    nuisance: float = 0.0) -> dict:
     """A data dict of the shape preprocess_adversary_data.py:20-38 writes (+ 'dataset', which combine_data adds :102):
-    z-normed-scale windows with class-dependent mean shifts so that emotion and gender are learnable."""
+    z-normed-scale windows with class-dependent mean shifts so that emotion and gender are learnable.
+    `nuisance` adds a per-utterance random offset to every band (std `nuisance`): it overlaps the class shifts, so the
+    classes are only partly separable and UAR / accuracy land strictly between chance and 1."""
     rng = np.random.default_rng(seed)
     out = {}
     for i in range(n):
@@ -86,6 +89,8 @@ def synthetic_split(n: int, seed: int, frames=(200, 200), shift: float = 0.5, n_
         emo, gen = int(rng.integers(4)), int(rng.integers(2))
         spk = int(rng.integers(n_speakers))
         x = rng.standard_normal((1, T, 128))
+        if nuisance:
+            x += nuisance * rng.standard_normal((1, 1, 128))
         x[:, :, 20 + 10 * emo: 30 + 10 * emo] += emo_shift
         x[:, :, 0:20] += shift if gen == 1 else -shift
         out[f"utt{seed}_{i}"] = {"data": x.astype(np.float64), "global_data": np.zeros((1, 88)), "label": EMO[emo],
@@ -133,14 +138,16 @@ class EpsTape:
     """Replaces `noise_model.normal.sample` -- the reference's own draw site (cloak_models.py:47,49) -- with a seeded
     tape so both variants see the same eps sequence ("eps supplied externally")."""
 
-    def __init__(self, seed: int, std: float = 0.1):
+    def __init__(self, seed: int, std: float = 0.1, ulp: bool = False):
         self.gen = torch.Generator().manual_seed(seed)
         self.std = std
         self.draws = 0
+        self.ulp = ulp                   # shift every sample by one unit in the last place: a rounding-sized perturbation
 
     def __call__(self, shape):
         self.draws += 1
-        return self.std * torch.randn(tuple(shape), generator=self.gen)
+        eps = self.std * torch.randn(tuple(shape), generator=self.gen)
+        return torch.nextafter(eps, torch.full_like(eps, float("inf"))) if self.ulp else eps
 
 
 def build_grl_model(mod, device, state=None, model_type="2d-cnn-lstm", att=None, hidden=64, max_scale=10.0, grl_lambda=0.1):
@@ -159,20 +166,25 @@ def build_grl_model(mod, device, state=None, model_type="2d-cnn-lstm", att=None,
 
 
 def run_grl_training(mod, device, train: dict, valid: dict, test: dict, *, state=None, epochs=2, batch_size=8, eps_seed=5,
-                     loader_seed=3, model_type="2d-cnn-lstm", att=None, hidden=64, record=None):
+                     loader_seed=3, model_type="2d-cnn-lstm", att=None, hidden=64, record=None, cloak_lr=0.001, scale_lamda=0,
+                     eps_ulp=False):
     """epochs x [train(training), train(validate), test()] of training_cloak_with_grl.py:430-436 on the given splits.
     Returns (per-epoch result dicts, final model).  `record`, if a list, receives every (preds, preds_grl) the model
     returned in training mode, in call order."""
-    args = make_args(batch_size=batch_size, num_epochs=epochs, model_type=model_type, att=att)
+    args = make_args(batch_size=batch_size, num_epochs=epochs, model_type=model_type, att=att, scale_lamda=scale_lamda)
     model = build_grl_model(mod, device, state, model_type, att, hidden)
     dropout_off(model)
-    tape = EpsTape(eps_seed) if eps_seed is not None else None      # None: the layer's own sampler (CPU normal / device Philox)
+    tape = EpsTape(eps_seed, ulp=eps_ulp) if eps_seed is not None else None   # None: the layer's own sampler (CPU normal / device Philox)
     if tape is not None:
         model.intermed.normal.sample = tape
     mod.weights = speaker_weights(mod.get_class_weight, train)
     mod.cloak_model = model
     loss = torch.nn.CrossEntropyLoss().to(device)
-    optimizer = torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=0.001, momentum=0.9, weight_decay=1e-4)
+    # :417 (SGD 1e-3, momentum 0.9, wd 1e-4); the cloak parameters may get their own learning rate so that a test of a few
+    # dozen steps moves them by more than rounding noise (their gradients are ~1e-5 per element)
+    cloak_params = list(model.intermed.parameters())
+    others = [p for p in model.parameters() if p.requires_grad and all(p is not q for q in cloak_params)]
+    optimizer = torch.optim.SGD([{"params": cloak_params, "lr": cloak_lr}, {"params": others}], lr=0.001, momentum=0.9, weight_decay=1e-4)
     mod.scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=10, gamma=0.5)
     hook = None
     if record is not None:
@@ -208,16 +220,16 @@ def build_syn_model(mod, device, state=None, att=None, hidden=64, max_scale=10.0
 
 
 def run_cloak_training(mod, device, train: dict, valid: dict, test: dict, *, state=None, epochs=1, batch_size=8, eps_seed=5,
-                       loader_seed=3, att=None, hidden=64, record=None):
+                       loader_seed=3, att=None, hidden=64, record=None, cloak_lr=0.001, scale_lamda=0):
     """training_cloak.py's train()/test() (no GRL; two_d_cnn_lstm_syn over deep_two_d_cnn_lstm, pooling None)."""
-    args = make_args(batch_size=batch_size, num_epochs=epochs, model_type="deep-2d-cnn-lstm", att=att)
+    args = make_args(batch_size=batch_size, num_epochs=epochs, model_type="deep-2d-cnn-lstm", att=att, scale_lamda=scale_lamda)
     model = build_syn_model(mod, device, state, att, hidden)
     dropout_off(model)
     tape = EpsTape(eps_seed)
     model.intermed.normal.sample = tape
     mod.weights = speaker_weights(mod.get_class_weight, train)
     loss = torch.nn.CrossEntropyLoss().to(device)
-    optimizer = torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=0.001, momentum=0.9, weight_decay=1e-4)
+    optimizer = torch.optim.SGD(filter(lambda p: p.requires_grad, model.parameters()), lr=cloak_lr, momentum=0.9, weight_decay=1e-4)
     mod.scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=10, gamma=0.5)
     hook = None
     if record is not None:

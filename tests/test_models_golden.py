@@ -133,21 +133,56 @@ def fp32_math():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+@pytest.fixture(scope="module")
+def reference_classes():
+    """The vendored reference model classes (tests/ref_fixture/model): run on the SAME GPU they separate the drop-in's
+    own error from the CPU-vs-GPU rounding of the stock conv / GRU / batch-norm kernels."""
+    import ref_harness as H
+    mod = H.load_driver("training_cloak", "reference")
+    ns = type("ns", (), {})
+    bm, cm = ns(), ns()
+    for k in ("two_d_cnn_lstm", "deep_two_d_cnn_lstm"):
+        setattr(bm, k, getattr(mod, k))
+    for k in ("cloak_noise", "two_d_cnn_lstm_syn", "two_d_cnn_lstm_syn_with_grl"):
+        setattr(cm, k, getattr(mod, k))
+    return bm, cm
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", META["wrappers"])
-def test_dropin_cloak_wrapper_equals_reference(golden, dropins, fp32_math, name):
+def test_dropin_cloak_wrapper_equals_reference(golden, dropins, reference_classes, fp32_math, name):
     wrapper, cls, att, pooling, use_mask, glob = _parse(name)
     model = G.build_wrapper(dropins[0], dropins[1], wrapper, cls, att, glob, device="cuda")
     out = G.run_wrapper(model, wrapper, pooling, bool(use_mask), glob, device="cuda")
-    _close(out["noisy_sub"], golden[f"{name}#noisy_sub"], 1e-6, "noisy")                # cloak forward: 1e-6 (north_star)
-    for k in ("eval_preds", "eval_preds_grl", "train_preds", "train_preds_grl"):
-        if k in out:
-            _close(out[k], golden[f"{name}#{k}"], 2e-4, k)
-    for k in ("dlocs_sub", "drhos_sub", "gender_conv0_wgrad", "gender_head_wgrad"):
-        if k in out:
-            _close(out[k], golden[f"{name}#{k}"], 2e-3, k)
-    assert abs(float(out["dlocs_sum"]) - float(golden[f"{name}#dlocs_sum"])) <= 2e-3 * max(1.0, float(golden[f"{name}#drhos_abs_sum"]))
     assert all(p.grad is None for p in model.original_model.parameters())
+    # (1) against the reference's own classes on the same GPU, same weights, same eps: only the fused cloak / gradient-
+    # reversal kernels differ, so the comparison is tight
+    ref = G.build_wrapper(reference_classes[0], reference_classes[1], wrapper, cls, att, glob, device="cuda")
+    want = G.run_wrapper(ref, wrapper, pooling, bool(use_mask), glob, device="cuda")
+    assert set(want) == set(out)
+    for k in want:
+        if k in ("dlocs_sum", "drhos_abs_sum"):
+            assert abs(float(out[k]) - float(want[k])) <= 1e-4 * max(1.0, abs(float(want[k]))), k
+        elif k == "noisy_sub":
+            _close(out[k], want[k], 1e-6, k)
+        elif "preds" in k:
+            _close(out[k], want[k], 2e-5, k + " vs reference on GPU")
+        else:
+            _close(out[k], want[k], 5e-4, k + " vs reference on GPU")
+    # (2) against the golden vectors of the real reference, computed on the CPU.  The cloak forward holds north_star's
+    # 1e-6.  Logits and gradients pass through the stock conv / GRU / batch-norm kernels, whose cuDNN and MKL versions
+    # round differently (train mode normalises with the statistics of a batch of 3, which amplifies it): the drop-in
+    # must be as close to the golden vectors as the reference's own classes are on this GPU
+    _close(out["noisy_sub"], golden[f"{name}#noisy_sub"], 1e-6, "noisy")
+    for k in want:
+        if k in ("dlocs_sum", "drhos_abs_sum", "noisy_sub"):
+            continue
+        gold = golden[f"{name}#{k}"]
+        scale = max(float(np.abs(gold).max()), 1e-6)
+        err_ref = float(np.abs(want[k] - gold).max()) / scale
+        err_new = float(np.abs(out[k] - gold).max()) / scale
+        assert err_new <= 1.5 * err_ref + 1e-5, (k, err_new, err_ref)
+        assert err_new <= (2e-3 if k.startswith("eval") else 0.2), (k, err_new)     # and the golden vectors are the right ones
 
 
 @pytest.mark.gpu

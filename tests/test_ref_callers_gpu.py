@@ -24,16 +24,19 @@ def world():
     tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.deterministic = True                       # what the reference's setup_seed() sets (:74)
-    tr, va = H.synthetic_split(96, 1), H.synthetic_split(24, 2)
-    te = H.synthetic_split(24, 3, frames=(200, 420))
+    # class shifts that overlap a per-utterance nuisance offset: the pretrained classifiers land at UAR ~0.8 / accuracy ~0.9
+    # (measured), so the scores below can move in both directions
+    kw = dict(emo_shift=0.4, shift=0.15, nuisance=0.5)
+    tr, va = H.synthetic_split(160, 1, **kw), H.synthetic_split(32, 2, **kw)
+    te = H.synthetic_split(48, 3, frames=(200, 420), **kw)
     base = H.load_driver("training_adversary_baselines", "reference")
     torch.manual_seed(8)
-    res_e, emo2d = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", epochs=6)
-    res_d, emodeep = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", model_type="deep-2d-cnn-lstm", epochs=6)
-    res_g, adv = H.run_baseline_training(base, dev, tr, va, te, pred="gender", epochs=3)
+    res_e, emo2d = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", epochs=8)
+    res_d, emodeep = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", model_type="deep-2d-cnn-lstm", epochs=8)
+    res_g, adv = H.run_baseline_training(base, dev, tr, va, te, pred="gender", epochs=6)
     # adversary_cloak_evaluation.py calls the cloak model without `pooling` (:79): only att='self_att' classifiers run (Appendix B)
-    res_ea, emo_att = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", att="self_att", epochs=6)
-    res_ga, adv_att = H.run_baseline_training(base, dev, tr, va, te, pred="gender", att="self_att", epochs=3)
+    res_ea, emo_att = H.run_baseline_training(base, dev, tr, va, te, pred="emotion", att="self_att", epochs=8)
+    res_ga, adv_att = H.run_baseline_training(base, dev, tr, va, te, pred="gender", att="self_att", epochs=6)
     REPORT["pretrained"] = {"emotion_2d_test_uar": res_e[-1]["test"]["combine"]["rec"]["emotion"],
                             "emotion_deep_test_uar": res_d[-1]["test"]["combine"]["rec"]["emotion"],
                             "adversary_test_acc": res_g[-1]["test"]["combine"]["acc"]["gender"]}
@@ -73,31 +76,58 @@ def test_grl_train_and_test_parity(world):
     H.build_grl_model(new, dev, state)                                             # strict load into the drop-in: same keys
 
     runs = {}
-    for tag, mod, eps_seed in (("ref_a", ref, 5), ("ref_b", ref, 6), ("new", new, 5), ("new_philox", new, None)):
+    for tag, mod, eps_seed in (("ref_a", ref, 5), ("ref_a2", ref, 5), ("ref_ulp", ref, 5), ("ref_b", ref, 6), ("new", new, 5),
+                               ("new_philox", new, None)):
         rec = []
         torch.manual_seed(8)
-        res, model, tape = H.run_grl_training(mod, dev, tr, va, te, state=state, epochs=2, batch_size=8, eps_seed=eps_seed, record=rec)
+        res, model, tape = H.run_grl_training(mod, dev, tr, va, te, state=state, epochs=2, batch_size=8, eps_seed=eps_seed, record=rec,
+                                              cloak_lr=0.2, scale_lamda=0.5, eps_ulp=(tag == "ref_ulp"))
         runs[tag] = {"res": res, "model": model, "rec": rec, "scores": _scores(res), "draws": None if tape is None else tape.draws}
     a, b, n, free = runs["ref_a"], runs["ref_b"], runs["new"], runs["new_philox"]
-    assert a["draws"] == n["draws"] and len(a["rec"]) == len(n["rec"]) == 2 * 12
+    assert a["draws"] == n["draws"] and len(a["rec"]) == len(n["rec"]) == 2 * 20
 
-    traj = max(max(float(np.abs(pa[0] - pn[0]).max()), float(np.abs(pa[1] - pn[1]).max())) for pa, pn in zip(a["rec"], n["rec"]))
+    logit_scale = max(1.0, max(float(np.abs(pa[0]).max()) for pa in a["rec"]), max(float(np.abs(pa[1]).max()) for pa in a["rec"]))
+    series = [max(float(np.abs(pa[0] - pn[0]).max()), float(np.abs(pa[1] - pn[1]).max())) / logit_scale for pa, pn in zip(a["rec"], n["rec"])]
+    traj = max(series)
+    traj_ab = max(float(np.abs(pa[0] - pb[0]).max()) for pa, pb in zip(a["rec"], b["rec"])) / logit_scale
+    series_emo = [float(np.abs(pa[0] - pn[0]).max()) / logit_scale for pa, pn in zip(a["rec"], n["rec"])]
+    # the reference against ITSELF, same seeds, same eps: bit-reproducible (cudnn.deterministic, as setup_seed() sets) ...
+    rerun = [max(float(np.abs(pa[0] - pn[0]).max()), float(np.abs(pa[1] - pn[1]).max())) / logit_scale for pa, pn in zip(a["rec"], runs["ref_a2"]["rec"])]
+    # ... but a ONE-ULP shift of eps already moves its logits by ~1e-4 of their scale within a step or two: train-mode batch-norm
+    # over 8 windows and the GRUs amplify rounding-sized input differences a thousandfold (scratch measurement: |d noisy| =
+    # 1.2e-7 -> |d logits| = 1e-4).  That is the resolution of any trajectory comparison on this network.
+    ulp = [max(float(np.abs(pa[0] - pn[0]).max()), float(np.abs(pa[1] - pn[1]).max())) / logit_scale for pa, pn in zip(a["rec"], runs["ref_ulp"]["rec"])]
     losses = max(abs(ra[s]["combine"]["loss"]["emotion"] - rn[s]["combine"]["loss"]["emotion"])
                  for ra, rn in zip(a["res"], n["res"]) for s in ("train", "validate"))
-    dl = float((a["model"].intermed.locs - n["model"].intermed.locs).abs().max())
-    dr = float((a["model"].intermed.rhos - n["model"].intermed.rhos).abs().max())
-    wa, wn = a["model"].gender_model.state_dict(), n["model"].gender_model.state_dict()
-    dw = max(float((wa[k].float() - wn[k].float()).abs().max()) for k in wa)
+    def final_diffs(other):
+        wa, wo = a["model"].gender_model.state_dict(), other["model"].gender_model.state_dict()
+        return (float((a["model"].intermed.locs - other["model"].intermed.locs).abs().max()),
+                float((a["model"].intermed.rhos - other["model"].intermed.rhos).abs().max()),
+                max(float((wa[k].float() - wo[k].float()).abs().max()) for k in wa))
+    dl, dr, dw = final_diffs(n)
+    ul, ur, uw = final_diffs(runs["ref_ulp"])
     moved = float((a["model"].intermed.locs - state["intermed.locs"]).abs().max())
     noise = _worst(a["scores"], b["scores"])
     one_sample = 1.0 / len(te)
-    REPORT["grl"] = {"steps": len(a["rec"]), "trajectory_max_abs_diff": traj, "epoch_loss_max_abs_diff": losses, "locs_diff": dl, "rhos_diff": dr,
-                     "gender_weights_diff": dw, "locs_moved_by_training": moved, "scores_ref_a": a["scores"], "scores_ref_b": b["scores"],
+    REPORT["grl"] = {"steps": len(a["rec"]), "max_abs_logit": logit_scale, "trajectory_max_diff_rel_to_logit_scale": traj,
+                     "trajectory_diff_between_two_eps_seeds": traj_ab, "per_step_diff": [float(f"{v:.3g}") for v in series],
+                     "per_step_diff_emotion_head": [float(f"{v:.3g}") for v in series_emo],
+                     "per_step_diff_reference_rerun": [float(f"{v:.3g}") for v in rerun],
+                     "per_step_diff_reference_with_eps_shifted_one_ulp": [float(f"{v:.3g}") for v in ulp],
+                     "epoch_loss_max_abs_diff": losses, "locs_diff": dl, "rhos_diff": dr,
+                     "gender_weights_diff": dw, "locs_rhos_weights_diff_of_one_ulp_reference": [ul, ur, uw],
+                     "locs_moved_by_training": moved, "scores_ref_a": a["scores"], "scores_ref_b": b["scores"],
                      "scores_dropin": n["scores"], "scores_dropin_philox": free["scores"], "run_to_run_noise": noise}
-    assert traj < 1e-4, traj                      # same eps, same batches: the logits of every training step agree
+    assert series[0] == 0.0 and max(rerun) == 0.0  # first step: bit-identical logits; the reference itself is reproducible
+    assert traj < 1e-4, traj                      # same eps, same batches: the logits of every training step agree to 1e-4 of their scale,
+    assert traj <= 3 * max(ulp) + 1e-6            # ... which is what a one-ulp perturbation of the reference's own eps does to it,
+    assert traj_ab > 10 * traj                    # ... and far closer than two reference runs that differ only in the eps seed
     assert losses < 1e-4, losses
-    assert dl < 1e-5 and dr < 1e-5 and dw < 1e-4, (dl, dr, dw)
-    assert moved > 1e-4                            # ... and training did move the cloak parameters
+    # final mu / rho / adversary weights: within 1 % of what training changed, and no further from the reference than its own
+    # one-ulp twin is
+    assert dl < 1e-2 * moved and dr < 1e-2 * moved, (dl, dr, moved)
+    assert dl <= 3 * ul + 1e-7 and dr <= 3 * ur + 1e-7 and dw <= 3 * uw + 1e-7, ((dl, dr, dw), (ul, ur, uw))
+    assert moved > 1e-3                            # ... and training did move the cloak parameters
     assert _worst(a["scores"], n["scores"]) <= max(noise, one_sample) + 1e-9          # UAR / accuracy within run-to-run noise
     # device Philox eps instead of the CPU tape (the production configuration): another noise realisation
     assert _worst(a["scores"], free["scores"]) <= max(2 * noise, 3 * one_sample) + 1e-9
@@ -118,15 +148,20 @@ def test_cloak_train_and_test_parity(world):
     for tag, mod, eps_seed in (("ref_a", ref, 5), ("ref_b", ref, 6), ("new", new, 5)):
         rec = []
         torch.manual_seed(8)
-        res, model, tape = H.run_cloak_training(mod, dev, tr, va, te, state=state, epochs=2, batch_size=8, eps_seed=eps_seed, record=rec)
+        res, model, tape = H.run_cloak_training(mod, dev, tr, va, te, state=state, epochs=2, batch_size=8, eps_seed=eps_seed, record=rec,
+                                                cloak_lr=0.2, scale_lamda=0.5)
         out[tag] = (res, model, rec, _scores(res))
-    traj = max(float(np.abs(pa - pn).max()) for pa, pn in zip(out["ref_a"][2], out["new"][2]))
+    logit_scale = max(1.0, max(float(np.abs(pa).max()) for pa in out["ref_a"][2]))
+    series = [float(np.abs(pa - pn).max()) / logit_scale for pa, pn in zip(out["ref_a"][2], out["new"][2])]
+    traj = max(series)
+    moved = float((out["new"][1].intermed.locs - state["intermed.locs"]).abs().max())
     dl = float((out["ref_a"][1].intermed.locs - out["new"][1].intermed.locs).abs().max())
     dr = float((out["ref_a"][1].intermed.rhos - out["new"][1].intermed.rhos).abs().max())
     noise = _worst(out["ref_a"][3], out["ref_b"][3])
-    REPORT["cloak"] = {"steps": len(out["new"][2]), "trajectory_max_abs_diff": traj, "locs_diff": dl, "rhos_diff": dr,
+    REPORT["cloak"] = {"steps": len(out["new"][2]), "trajectory_max_diff_rel_to_logit_scale": traj, "locs_diff": dl, "rhos_diff": dr,
+                       "locs_moved_by_training": moved, "per_step_diff": [float(f"{v:.3g}") for v in series],
                        "scores_ref_a": out["ref_a"][3], "scores_dropin": out["new"][3], "run_to_run_noise": noise}
-    assert traj < 1e-4 and dl < 1e-5 and dr < 1e-5, (traj, dl, dr)
+    assert traj < 1e-4 and moved > 1e-3 and dl < 1e-2 * moved and dr < 1e-2 * moved, (traj, dl, dr, moved)
     assert _worst(out["ref_a"][3], out["new"][3]) <= max(noise, 1.0 / len(te)) + 1e-9
     world["syn_state"] = copy.deepcopy(out["new"][1].state_dict())
 
