@@ -6,8 +6,9 @@
 
 One step = one pass of the extraction hot path over one corpus-sized ragged batch (5531 utterances, 2-10 s each,
 ~9.2 audio-hours, 2.1 GB of fp32 waveform -- larger than the 126 MB L2, so no flush is needed between steps).
-N > 1 (torchrun, one rank per GPU): every rank extracts its own corpus-sized shard, no data-path collective
-("scaling": "weak"); the time is the max over ranks of the CUDA-event time of the K steps.
+N > 1 (torchrun, one rank per GPU): ONE corpus of N x 5531 utterances is length-bucketed and dealt to the ranks by
+parallel.shard_by_length (every rank gets the same mix of lengths and the same amount of audio), no data-path collective
+("scaling": "weak": the audio per GPU is fixed); the time is the max over ranks of the CUDA-event time of the K steps.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
 """
@@ -134,10 +135,10 @@ class ClockSampler:
 def profiled_traffic(frames: int):
     """DRAM bytes per launch of the extraction kernel from the committed ncu capture (profiles/), scaled per frame when
     the workload size differs; None if no capture is committed."""
-    p = REPO / "profiles" / "extract800_traffic_r01.json"
-    if N_FFT != 800 or not p.exists():
+    cands = sorted((REPO / "profiles").glob("extract800_traffic_r*.json"))
+    if N_FFT != 800 or not cands:
         return None
-    t = json.loads(p.read_text())
+    t = json.loads(cands[-1].read_text())                       # the newest capture; regenerate it whenever extract.cu changes
     return int((t["dram_bytes_read"] + t["dram_bytes_write"]) * frames / t["frames"])
 
 
@@ -201,7 +202,8 @@ def workload_config(world: int, note: str | None = None):
                        f"IEMOCAP-sized corpus: {CORPUS_UTTS} utterances of 2-10 s at 16 kHz per GPU (BASELINE.json configs[0] "
                        "shape, batched as in configs[3])",
            "utterances_per_gpu": CORPUS_UTTS, "n_fft": N_FFT, "hop": HOP, "n_mels": N_MELS,
-           "layout": "frame-major (T,128) per utterance", "sharding": f"utterances, {world} rank(s), no collective",
+           "layout": "frame-major (T,128) per utterance",
+           "sharding": f"one corpus of {CORPUS_UTTS * world} utterances dealt to {world} rank(s) by length bucket (parallel.shard_by_length), no collective",
            "l2": "inputs (2.1 GB/step) larger than L2, no flush needed"}
     if note:
         cfg["note"] = note
@@ -230,7 +232,12 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().sept_init(N_MELS))
 
-    lengths = corpus_lengths(args.utts, 1234 + rank)
+    from speech_emotion_privacy_trust_b200 import parallel
+    placement = parallel.bind_host_to_gpu(local)                  # before any pinned allocation (host-buffer path)
+    all_lengths = corpus_lengths(args.utts * world, 1234)        # ONE corpus for the whole job ...
+    shards = parallel.shard_by_length(all_lengths, world)        # ... length-bucketed (0.5 s) and balanced over the ranks
+    lengths = all_lengths[shards[rank]]
+    shard_audio = np.array([all_lengths[sh].sum() for sh in shards], dtype=np.float64)
     if args.round_lengths > 1:                                    # debug only: every utterance starts on an aligned sample
         lengths = (lengths // args.round_lengths) * args.round_lengths
     utt_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
@@ -274,15 +281,22 @@ def run_b200(args):
         e2e_ms = measure_e2e(args, extraction, wav, utt_off, frames, out, dev, barrier)
     # ---- max over ranks --------------------------------------------------------------------------------------
     stats = torch.tensor([total_ms, e2e_ms, hours, float(frames)], dtype=torch.float64, device=dev)
+    rank_ms = [total_ms / args.steps]
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        every = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(every, stats)
+        rank_ms = [float(t[0]) / args.steps for t in every]
         total_ms, e2e_ms = float(mx[0]), float(mx[1])
         hours_all, frames_all = float(sm[2]), float(sm[3])
     else:
         hours_all, frames_all = hours, float(frames)
+    sharding = {"policy": "parallel.shard_by_length: one corpus, 0.5 s length buckets, longest-first greedy balance",
+                "utterances_total": int(args.utts * world), "audio_hours_per_rank_max_over_mean": float(shard_audio.max() / shard_audio.mean()),
+                "rank_ms_per_step_max": max(rank_ms), "rank_ms_per_step_mean": sum(rank_ms) / len(rank_ms), "host_placement": placement}
 
     extras = {}
     if args.no_extras:
@@ -305,6 +319,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
+            "sharding": sharding,
             "clocks": clocks,
             "e2e": None if args.no_extras else {"value": hours_all / (e2e_ms * 1e-3), "unit": "audio-hours/s", "h2d_bytes_per_step": int(wav.numel() * 4),
                     "d2h_bytes_per_step": int(frames * N_MELS * 4), "ms_per_step": e2e_ms,
@@ -315,7 +330,8 @@ def run_b200(args):
                         "note": "same call with 16-bit PCM host input (x/32768 on the device, as torchaudio.load does on the host)"}},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                         "traffic": profiled_traffic(frames), "algorithmic_bytes": BYTES_PER_FRAME * frames, "kernel": "extract_kernel<16, frame-major>", "kernel_ms": k_ms,
+                         "traffic": profiled_traffic(frames), "traffic_source": "ncu --set full capture under profiles/ (dram__bytes_read+write of one launch, scaled by frames); not measured in this run",
+                         "algorithmic_bytes": BYTES_PER_FRAME * frames, "kernel": "extract_kernel<16, frame-major>", "kernel_ms": k_ms,
                          "algorithmic_flop_per_frame": FLOP_PER_FRAME, "frames_per_launch": frames,
                          "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json ({peak_src}); "
                                         "the path is FP32-CUDA-core bound, not HBM or tensor bound (SURVEY 8d)",
@@ -391,7 +407,91 @@ def secondary_metrics(args, dev, rank, world, batch=None, hours=None):
             out["cloak_eval_cpu_baseline"] = eval_cpu_baseline()
     if batch is not None:
         out["other_features_this_rank"] = other_features(batch, hours, dev)
+    if world > 1:
+        out["speaker_stats_nccl_check"] = speaker_stats_nccl_check(dev, rank, world)
+    if not args.no_bulk:
+        bulk = bulk_extraction(dev, rank, world, args.bulk_hours)
+        if rank == 0:
+            out["bulk_extraction"] = bulk
     return out
+
+
+def speaker_stats_nccl_check(dev, rank, world, n_utts=64, n_spk=10, seed=99):
+    """SURVEY 8e row 2 on hardware: per-speaker statistics when every speaker's utterances are spread over the ranks
+    (one NCCL all-gather of the partials + Chan merge) equal the statistics one rank computes over all utterances."""
+    import torch.distributed as dist
+    from speech_emotion_privacy_trust_b200 import normalization as nz, parallel
+    from speech_emotion_privacy_trust_b200.extraction import Layout
+    rng = np.random.default_rng(seed)                              # the same data on every rank
+    frames = rng.integers(201, 1002, size=n_utts)
+    spk = [f"s{int(rng.integers(n_spk))}" for _ in range(n_utts)]
+    feats = [(rng.standard_normal((int(T), 128)) * 8 - 40).astype(np.float32) for T in frames]
+    speakers = sorted(set(spk))
+
+    def stats_of(idx, distributed):
+        fo = np.concatenate([[0], np.cumsum([frames[i] for i in idx])]).astype(np.int64)
+        lay = Layout(fo, torch.from_numpy(fo).to(dev), torch.zeros(len(fo), dtype=torch.int32, device=dev))
+        feat = torch.from_numpy(np.concatenate([feats[i] for i in idx])).to(dev)
+        who = [spk[i] for i in idx]
+        return nz.speaker_stats_distributed(feat, lay, who, speakers) if distributed else nz.speaker_stats(feat, lay, who)
+    mine = [int(i) for i in parallel.shard_by_length(frames * 160, world)[rank]]
+    got = stats_of(mine, True).as_dict()
+    want = stats_of(list(range(n_utts)), False).as_dict()
+    worst = 0.0
+    for s_ in speakers:
+        for k in ("count", "mean", "std", "min", "max"):
+            worst = max(worst, float(np.max(np.abs(got[s_][k] - want[s_][k]))))
+    t = torch.tensor([worst], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst = float(t)
+    if worst > 1e-3:
+        raise SystemExit(f"bench.py: distributed speaker statistics differ from the single-rank ones by {worst}")
+    return {"speakers": len(speakers), "utterances": n_utts, "max_abs_diff_vs_single_rank": worst, "collective": "all_gather of (count, mean, M2, min, max) partials"}
+
+
+def bulk_extraction(dev, rank, world, total_hours=1000.0, chunk_utts=CORPUS_UTTS):
+    """BASELINE.json configs[3]: bulk log-mel extraction of `total_hours` synthetic audio-hours (600 000 utterances of
+    2-10 s for 1000 h), length-bucketed and sharded over the ranks by parallel.shard_by_length.  1000 h of fp32 waveform
+    (230 GB) exceed one GPU, so every rank synthesises its shard on the device in corpus-sized chunks (2.1 GB), extracts
+    the chunk (one launch, timed with CUDA events) and drops it; the figure is total audio-hours over the slowest rank's
+    summed kernel time -- strong scaling of a fixed job, inputs resident in HBM."""
+    import torch.distributed as dist
+    from speech_emotion_privacy_trust_b200 import extraction, parallel
+    n_utts = int(round(total_hours * 600))                         # mean 6 s
+    lengths = corpus_lengths(n_utts, 4321)
+    t0 = time.perf_counter()
+    mine = lengths[parallel.shard_by_length(lengths, world)[rank]]
+    t_shard = time.perf_counter() - t0
+    out = None
+    ms, frames, n_launch = 0.0, 0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for c, a in enumerate(range(0, len(mine), chunk_utts)):
+        lens = mine[a:a + chunk_utts]
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        batch = extraction.RaggedAudio(synth_corpus_device(lens, 777 + 1000 * rank + c, dev), off)
+        lay = batch.layout(800, 160)
+        if out is None or out.shape[0] < lay.total_frames:
+            out = torch.empty((int(lay.total_frames * 1.05), N_MELS), dtype=torch.float32, device=dev)
+        if c == 0:
+            extraction.logmel(batch, n_fft=800, n_mels=N_MELS, hop=160, out=out[:lay.total_frames])     # warm
+        e0.record()
+        extraction.logmel(batch, n_fft=800, n_mels=N_MELS, hop=160, out=out[:lay.total_frames])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms += e0.elapsed_time(e1)
+        frames += lay.total_frames
+        n_launch += 1
+        del batch
+    t = torch.tensor([ms, float(mine.sum()) / 16000 / 3600, float(frames)], dtype=torch.float64, device=dev)
+    mx, sm = t.clone(), t.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    hours = float(sm[1])
+    return {"workload": f"{hours:.0f} audio-hours, {n_utts} utterances of 2-10 s, length-bucketed over {world} rank(s), chunks of {chunk_utts} utterances synthesised on the device",
+            "audio_hours": hours, "kernel_ms_slowest_rank": float(mx[0]), "kernel_ms_mean_rank": float(sm[0]) / world,
+            "audio_hours_per_s": hours / (float(mx[0]) * 1e-3), "launches_this_rank": n_launch, "frames_total": float(sm[2]),
+            "host_sharding_s": t_shard, "scaling": "strong"}
 
 
 def other_features(batch, hours, dev, steps=5):
@@ -443,6 +543,8 @@ def main():
     ap.add_argument("--n-fft", type=int, default=N_FFT, help="debug only: time another FFT size (the metric is quoted on 800)")
     ap.add_argument("--round-lengths", type=int, default=1, help="debug only: round utterance lengths down to a multiple (alignment experiments)")
     ap.add_argument("--utts", type=int, default=CORPUS_UTTS, help="utterances per GPU (debug only; the metric is quoted on the default)")
+    ap.add_argument("--no-bulk", action="store_true", help="skip the 1000-audio-hour bulk extraction (BASELINE.json configs[3]) in extras")
+    ap.add_argument("--bulk-hours", type=float, default=1000.0, help="size of the bulk extraction job in extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

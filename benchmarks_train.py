@@ -48,7 +48,7 @@ def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_la
     if graphs:
         from speech_emotion_privacy_trust_b200.train_step import GraphedTrainStep
         example = [hx[:batch].to(dev), hemo[:batch].to(dev), hgen[:batch].to(dev), w]
-        graphed = GraphedTrainStep(model, opt, loss_fn, example, allreduce=parallel.allreduce_gradients if world > 1 else None)
+        graphed = GraphedTrainStep(model, opt, loss_fn, example, data_parallel=world > 1)
 
     def step(i):
         s = (i % 4) * batch
@@ -88,7 +88,8 @@ def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_la
     n_params = sum(p.numel() for p in params)
     return {"metric": "cloak+GRL train utterances/sec", "value": batch * world * steps / (ms * 1e-3), "unit": "utterances/s",
             "ms_per_step": ms / steps, "per_gpu_batch": batch, "global_batch": batch * world, "steps": steps,
-            "model": "two_d_cnn_lstm_syn_with_grl(two_d_cnn_lstm h=64 x2)", "memory_format": "channels_last" if channels_last else "contiguous", "cuda_graphs": bool(graphs), "trainable_params": n_params,
+            "model": "two_d_cnn_lstm_syn_with_grl(two_d_cnn_lstm h=64 x2)", "graphs_per_step": (1 if graphed is not None and graphed.single_graph else (2 if graphed is not None else 0)),
+            "allreduce": ("NCCL AVG of the flat gradient buffer, captured inside the step graph" if (graphed is not None and graphed.single_graph) else "flat gradient buffer, eager") if world > 1 else None, "memory_format": "channels_last" if channels_last else "contiguous", "cuda_graphs": bool(graphs), "trainable_params": n_params,
             "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0, "final_loss": float(loss_host[0]),
             "h2d_bytes_per_step": int(batch * 200 * 128 * 4 + batch * 16), "includes": "H2D batch, fwd, bwd, all-reduce, SGD, loss D2H"}
 

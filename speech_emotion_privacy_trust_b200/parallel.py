@@ -53,6 +53,55 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, averag
     return off
 
 
+class FlatGradients:
+    """One persistent fp32 buffer that IS the gradients: every trainable parameter's `.grad` is a view into it (same
+    sizes and strides as the parameter, so channels_last weights keep their layout).  Autograd accumulates into existing
+    `.grad` tensors in place, so after backward the buffer holds every gradient back to back -- the data-parallel
+    exchange is ONE all-reduce of `flat` with no `torch.cat` before it and no copy-back after it, `zero()` is one memset,
+    and all three are fixed-address operations that a CUDA graph can capture together with backward and the optimizer.
+
+    Do not call `optimizer.zero_grad(set_to_none=True)` while this is in use: it would detach the views (`check()` tells)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        if any(p.dtype != torch.float32 for p in self.params):
+            raise ValueError("FlatGradients holds fp32 gradients (the reference trains in fp32)")
+        dev = self.params[0].device
+        self.offsets = []
+        total = 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += p.numel()
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, self.offsets):
+            dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
+            p.grad = (torch.as_strided(self.flat, p.size(), p.stride(), off) if dense
+                      else self.flat[off:off + p.numel()].view(p.shape))
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def check(self) -> bool:
+        """True while every .grad still aliases the buffer."""
+        base = self.flat.data_ptr()
+        return all(p.grad is not None and p.grad.data_ptr() == base + 4 * off for p, off in zip(self.params, self.offsets))
+
+    def allreduce(self, group=None, average: bool = True) -> int:
+        """Sum (mean) the buffer over the ranks in place; returns the number of elements exchanged (0 on one rank)."""
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return 0
+        world = dist.get_world_size(group)
+        if average and dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # the division happens inside the collective
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                self.flat.mul_(1.0 / world)
+        return self.flat.numel()
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
     """Make every rank start from rank `src`'s parameters and buffers."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -84,3 +133,42 @@ def merge_speaker_partials(count: torch.Tensor, mean: torch.Tensor, m2: torch.Te
         lo, hi = torch.minimum(lo, lb), torch.maximum(hi, hb)
     std = torch.sqrt(s2 / torch.where(n > 0, n, torch.ones_like(n)))
     return n, mu, std, lo, hi
+
+
+# ---- host placement: the end-to-end (host buffer) path is bound by PCIe and by the host's memory fabric --------------
+def bind_host_to_gpu(device_index: int) -> dict | None:
+    """Pin the calling thread to the CPUs NVML reports as local to the GPU and prefer that NUMA node for the memory it
+    allocates from now on (pinned staging buffers are first-touched by this thread).  Call it before allocating pinned
+    host memory.  Returns {"cpus": [...], "node": n} or None when the platform exposes no topology (then nothing changes)."""
+    import ctypes
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return None                                            # one domain: nothing to choose
+        os.sched_setaffinity(0, cpus)
+        node = None
+        for entry in os.listdir(f"/sys/devices/system/cpu/cpu{cpus[0]}"):
+            if entry.startswith("node") and entry[4:].isdigit():
+                node = int(entry[4:])
+        if node is not None:
+            libc = ctypes.CDLL(None, use_errno=True)
+            nodemask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238            # x86_64
+            libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(nodemask), ctypes.c_ulong(64))
+        return {"cpus": cpus, "node": node}
+    except Exception:
+        return None

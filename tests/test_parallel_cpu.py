@@ -72,6 +72,28 @@ def _worker(rank, world, port, out):
         n_, mu, sd, lo, hi = parallel.merge_speaker_partials(cnt, mean, m2, mine.amin(1), mine.amax(1))
         ok = ok and torch.allclose(mu, torch.from_numpy(data.mean(1))) and torch.allclose(sd, torch.from_numpy(data.std(1)))
         ok = ok and torch.equal(lo, torch.from_numpy(data.min(1))) and torch.equal(hi, torch.from_numpy(data.max(1))) and float(n_[0, 0]) == 40.0
+        # FlatGradients: .grad are views of one buffer; two data-parallel SGD steps == two full-batch steps in one process
+        torch.manual_seed(1)
+        net = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.Linear(4 * 6 * 6, 3))
+        net = net.to(memory_format=torch.channels_last)
+        torch.manual_seed(1)
+        full = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.Linear(4 * 6 * 6, 3))
+        xi, yi = torch.randn(8, 1, 6, 6, generator=g), torch.randn(8, 3, generator=g)
+        fg = parallel.FlatGradients(net.parameters())
+        opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+        opt_full = torch.optim.SGD(full.parameters(), lr=0.1, momentum=0.9)
+        ok = ok and fg.check() and all(p.grad.stride() == p.stride() for p in net.parameters())
+        for _ in range(2):
+            fg.zero()
+            ((net(xi[rank * 4:(rank + 1) * 4]) - yi[rank * 4:(rank + 1) * 4]) ** 2).mean().backward()
+            ok = ok and fg.check()                                        # autograd accumulated in place: still views
+            ok = ok and fg.allreduce() == sum(p.numel() for p in net.parameters())
+            opt.step()
+            opt_full.zero_grad()
+            ((full(xi) - yi) ** 2).mean().backward()
+            opt_full.step()
+        for a, b in zip(net.parameters(), full.parameters()):
+            ok = ok and torch.allclose(a, b, atol=1e-6)
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
