@@ -68,7 +68,12 @@ def lib() -> C.CDLL:
                         raise RuntimeError(f"{path.name} is {state} and cannot be rebuilt: {exc}") from exc
         handle = C.CDLL(str(path))
         for name, (res, args) in _SIGNATURES.items():
-            fn = getattr(handle, name)
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                if override:                                       # an older experimental build: A/B timing only
+                    continue
+                raise
             fn.restype, fn.argtypes = res, args
         if not override:
             got = handle.sept_source_hash().decode().split("=", 1)[1]
