@@ -62,8 +62,14 @@ class FlatGradients:
 
     Do not call `optimizer.zero_grad(set_to_none=True)` while this is in use: it would detach the views (`check()` tells)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params: Iterable[torch.nn.Parameter], early: Iterable[torch.nn.Parameter] = ()):
+        """`early`: parameters whose gradients are complete first in backward (the layers nearest the loss).  They are laid
+        out at the front of the buffer as their own bucket, so that bucket can be reduced on a side stream while backward
+        still runs through the earlier layers (`allreduce_early` / `allreduce_late`)."""
+        params = [p for p in params if p.requires_grad]
+        early_ids = {id(p) for p in early}
+        self.params = [p for p in params if id(p) in early_ids] + [p for p in params if id(p) not in early_ids]
+        self.n_early_params = sum(1 for p in params if id(p) in early_ids)
         if not self.params:
             raise ValueError("no trainable parameters")
         if any(p.dtype != torch.float32 for p in self.params):
@@ -75,6 +81,7 @@ class FlatGradients:
             self.offsets.append(total)
             total += p.numel()
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.early_numel = sum(p.numel() for p in self.params[:self.n_early_params])
         for p, off in zip(self.params, self.offsets):
             dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
             p.grad = (torch.as_strided(self.flat, p.size(), p.stride(), off) if dense
@@ -88,18 +95,29 @@ class FlatGradients:
         base = self.flat.data_ptr()
         return all(p.grad is not None and p.grad.data_ptr() == base + 4 * off for p, off in zip(self.params, self.offsets))
 
-    def allreduce(self, group=None, average: bool = True) -> int:
-        """Sum (mean) the buffer over the ranks in place; returns the number of elements exchanged (0 on one rank)."""
-        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    def _reduce(self, t: torch.Tensor, group, average: bool) -> int:
+        if t.numel() == 0 or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return 0
         world = dist.get_world_size(group)
         if average and dist.get_backend(group) == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # the division happens inside the collective
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)              # the division happens inside the collective
         else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
             if average:
-                self.flat.mul_(1.0 / world)
-        return self.flat.numel()
+                t.mul_(1.0 / world)
+        return t.numel()
+
+    def allreduce(self, group=None, average: bool = True) -> int:
+        """Sum (mean) the buffer over the ranks in place; returns the number of elements exchanged (0 on one rank)."""
+        return self._reduce(self.flat, group, average)
+
+    def allreduce_early(self, group=None, average: bool = True) -> int:
+        """The bucket of the `early` parameters (call it as soon as their gradients are complete)."""
+        return self._reduce(self.flat[:self.early_numel], group, average)
+
+    def allreduce_late(self, group=None, average: bool = True) -> int:
+        """Everything behind the early bucket."""
+        return self._reduce(self.flat[self.early_numel:], group, average)
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

@@ -94,6 +94,23 @@ def _worker(rank, world, port, out):
             opt_full.step()
         for a, b in zip(net.parameters(), full.parameters()):
             ok = ok and torch.allclose(a, b, atol=1e-6)
+        # two buckets: the layer nearest the loss sits at the front of the buffer and is reduced on its own
+        # (train_step.GraphedTrainStep overlaps that exchange with the rest of backward); early + late == one bucket
+        torch.manual_seed(1)
+        net2 = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.Linear(4 * 6 * 6, 3))
+        for p in net2.parameters():
+            p.grad = None
+        fg2 = parallel.FlatGradients(net2.parameters(), early=list(net2[3].parameters()))
+        ok = ok and fg2.check() and fg2.n_early_params == 2 and fg2.early_numel == 4 * 6 * 6 * 3 + 3
+        ok = ok and fg2.params[0] is net2[3].weight and fg2.params[2] is net2[0].weight
+        fg2.zero()
+        ((net2(xi[rank * 4:(rank + 1) * 4]) - yi[rank * 4:(rank + 1) * 4]) ** 2).mean().backward()
+        ok = ok and fg2.allreduce_early() == fg2.early_numel and fg2.allreduce_late() == fg2.flat.numel() - fg2.early_numel
+        torch.manual_seed(1)
+        full2 = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.Linear(4 * 6 * 6, 3))
+        ((full2(xi) - yi) ** 2).mean().backward()
+        for a, b in zip(net2.parameters(), full2.parameters()):
+            ok = ok and torch.allclose(a.grad, b.grad, atol=1e-6)
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
