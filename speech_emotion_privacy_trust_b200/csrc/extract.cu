@@ -6,7 +6,7 @@
 //                             and the finished features.  FAST (the reference's 128-band filterbank): the lane-constant
 //                             tables -- window samples, split twiddles, mel program -- live in tensor memory (tmem.cuh)
 //                             and the mel phase is unrolled; otherwise they are read from shared memory.
-//   mfcc_dct_kernel           second phase of MFCC: per-utterance top_db floor + ortho DCT-II (folded, frame pairs).
+//   (the second phase of MFCC -- per-utterance top_db floor + ortho DCT-II -- lives in mfcc_dct.cu / mfcc_tc.cu)
 //
 // Replaces torchaudio MelSpectrogram/AmplitudeToDB/MFCC as called by
 // feature_extraction/audio_feature_extraction.py:15-46 of the reference.
@@ -464,128 +464,6 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 }
 
 
-// ---- MFCC phase 2: dB with the per-utterance floor, then DCT (transforms/_transforms.py:714-717) ------------
-// One CTA handles kDctFrames = 64 consecutive global frames (they may straddle utterances).  The load phase converts the
-// two mel-power streams to dB in shared memory, clamped at the top_db floor of their utterance.  Thread (f = tid % 32, q = tid / 32) then produces
-// coefficients [10q, 10q+10) of the three streams for the frame PAIR (f, f + 32) packed in pk2 (30 packed accumulators;
-// the weights are fetched once per two frames).  The ortho DCT-II basis is symmetric, D[127-m][c] = (-1)^c D[m][c], so
-// bands m and 127-m are folded first: even coefficients take x[m] + x[127-m], odd ones the difference -- 15 + 15 FFMA2
-// per band pair instead of 60, and only half of the basis in shared memory.  Stream 2 (np.gradient(x, 2) ==
-// np.gradient(x) / 2 exactly, a quarter of stream 1's power) is derived on the fly: its dB and its floor are stream 1's
-// minus 10 log10(4), so it is the clamped stream 1 minus 10 log10(4), clamped again at amplitude_to_DB's amin (-100 dB).  Rows of the dB tile are rotated by the
-// frame index instead of padded (conflict-free scalar reads, exactly 64 KB), which lets three CTAs share an SM.
-constexpr int kDctFrames = 64;
-constexpr int kDctThreads = 128;
-constexpr int kDctNM = 128, kDctNC = 40, kDctDS = 40, kDctHalf = kDctNM / 2;
-constexpr size_t kDctSmem = (kDctHalf * kDctDS + 2 * kDctFrames * kDctNM + 4 * kDctFrames) * 4;   // 75 KB
-constexpr float kDbQuarter = 6.02059991327962390f;     // 10 log10(4)
-
-__global__ void __launch_bounds__(kDctThreads, 3) mfcc_dct_kernel(const MfccDctParams prm) {
-    constexpr int NM = kDctNM, NC = kDctNC, DS = kDctDS;
-    extern __shared__ __align__(16) unsigned char dct_smem[];
-    float* D = reinterpret_cast<float*>(dct_smem);                                   // [NM / 2][DS]: basis rows 0..63
-    float* X = D + kDctHalf * DS;                                                    // [2][kDctFrames][NM] dB, unclamped; band m of
-                                                                                     // frame f at column (m + f) % NM
-    int* frame_utt = reinterpret_cast<int*>(X + 2 * kDctFrames * NM);                // [kDctFrames]
-    float* frame_floor = reinterpret_cast<float*>(frame_utt + kDctFrames);           // [3][kDctFrames]
-    const long long g0 = (long long)blockIdx.x * kDctFrames;
-    for (int i = threadIdx.x; i < kDctHalf * NC / 4; i += kDctThreads)
-        reinterpret_cast<float4*>(D)[i] = reinterpret_cast<const float4*>(prm.dct)[i];
-    if (threadIdx.x < kDctFrames) {
-        const long long g = g0 + threadIdx.x;
-        const int lo_ = g < prm.total_frames ? prm.frame_utt[g] : 0;
-        frame_utt[threadIdx.x] = lo_;
-        const float max0 = __int_as_float(prm.utt_max[lo_]), max1 = __int_as_float(prm.utt_max[prm.n_utts + lo_]);
-        frame_floor[threadIdx.x] = power_to_db(max0) - prm.top_db;
-        frame_floor[kDctFrames + threadIdx.x] = power_to_db(max1) - prm.top_db;
-        // power_to_db(p / 4) = max(power_to_db(p) - 10 log10 4, -100): the amin clamp rides on the floor
-        frame_floor[2 * kDctFrames + threadIdx.x] = fmaxf(power_to_db(0.25f * max1) - prm.top_db, -100.0f);
-    }
-    // load phase: 16 float4 loads of a thread are issued before the first is used; a warp covers 4 frames x 8 quads per
-    // step (128-byte segments in HBM, and 32 distinct banks for its scalar stores into the rotated rows)
-    {
-        constexpr int NIT = 16, PASSES = 2 * kDctFrames * (NM / 4) / kDctThreads / NIT;   // 2 passes of 16
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int f_lo = lane >> 3, m4_lo = lane & 7;
-#pragma unroll 1
-        for (int pass = 0; pass < PASSES; ++pass) {
-            float4 pw[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int combo = (pass * NIT + it) * 4 + warp, s = combo >> 6, rem = combo & 63;
-                const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
-                const long long g = g0 + f;
-                pw[it] = g < prm.total_frames
-                             ? __ldg(reinterpret_cast<const float4*>(prm.power + ((long long)s * prm.total_frames + g) * NM) + m4)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (pass == 0) __syncthreads();                                          // frame_floor is ready (the loads are in flight)
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int combo = (pass * NIT + it) * 4 + warp, s = combo >> 6, rem = combo & 63;
-                const int f = (rem >> 2) * 4 + f_lo, m4 = (rem & 3) * 8 + m4_lo;
-                float* x = X + (s * kDctFrames + f) * NM;
-                const int col = 4 * m4 + f;
-                const float fl = frame_floor[s * kDctFrames + f];                    // top_db floor of the frame's utterance
-                x[col & (NM - 1)] = fmaxf(power_to_db(pw[it].x), fl); x[(col + 1) & (NM - 1)] = fmaxf(power_to_db(pw[it].y), fl);
-                x[(col + 2) & (NM - 1)] = fmaxf(power_to_db(pw[it].z), fl); x[(col + 3) & (NM - 1)] = fmaxf(power_to_db(pw[it].w), fl);
-            }
-        }
-    }
-    __syncthreads();
-    const int f = threadIdx.x & 31, q = threadIdx.x >> 5;
-    pk2 acc[3][10];
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-#pragma unroll
-        for (int c = 0; c < 10; ++c) acc[s][c] = splat(0.f);
-    const float* xa0 = X + f * NM;                                                   // frame f, stream 0 (rotated by f)
-    const float* xb0 = xa0 + 32 * NM;                                                // frame f + 32 (rotated by f + 32)
-    const float* xa1 = xa0 + kDctFrames * NM;
-    const float* xb1 = xb0 + kDctFrames * NM;
-    const float* drow = D + 10 * q;
-    auto max2 = [](pk2 a, pk2 b) { return pk(fmaxf(lo(a), lo(b)), fmaxf(hi(a), hi(b))); };
-#pragma unroll 2
-    for (int m = 0; m < kDctHalf; ++m) {
-        const int ca = (m + f) & (NM - 1), cb = (m + f + 32) & (NM - 1);             // band m of the two frames
-        const int ma = (NM - 1 - m + f) & (NM - 1), mb = (NM - 1 - m + f + 32) & (NM - 1);   // band 127 - m
-        const pk2 r0 = pk(xa0[ca], xb0[cb]), r1 = pk(xa1[ca], xb1[cb]);
-        const pk2 t0 = pk(xa0[ma], xb0[mb]), t1 = pk(xa1[ma], xb1[mb]);
-        // streams 0 and 1 were clamped in the load phase; stream 2 = max(dB1 - 10 log10 4, floor1 - 10 log10 4, -100)
-        //                                                           = max(clamped dB1 - 10 log10 4, -100)
-        const pk2 d0 = r0, d1 = r1, d2 = max2(r1 - splat(kDbQuarter), splat(-100.0f));
-        const pk2 u0 = t0, u1 = t1, u2 = max2(t1 - splat(kDbQuarter), splat(-100.0f));
-        const pk2 e[3] = {d0 + u0, d1 + u1, d2 + u2}, o[3] = {d0 - u0, d1 - u1, d2 - u2};
-        const float2 w01 = *reinterpret_cast<const float2*>(drow + m * DS);
-        const float2 w23 = *reinterpret_cast<const float2*>(drow + m * DS + 2);
-        const float2 w45 = *reinterpret_cast<const float2*>(drow + m * DS + 4);
-        const float2 w67 = *reinterpret_cast<const float2*>(drow + m * DS + 6);
-        const float2 w89 = *reinterpret_cast<const float2*>(drow + m * DS + 8);
-        const float w[10] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w89.x, w89.y};
-#pragma unroll
-        for (int c = 0; c < 10; ++c) {                                               // 10 q is even: coefficient parity = c parity
-            const pk2 wc = splat(w[c]);
-#pragma unroll
-            for (int s = 0; s < 3; ++s) acc[s][c] = fma2((c & 1) ? o[s] : e[s], wc, acc[s][c]);
-        }
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int fr = f + 32 * half;
-        const long long g = g0 + fr;
-        if (g >= prm.total_frames) continue;
-        const int u = frame_utt[fr];
-        const long long f0 = prm.frame_off[u];
-        const int T = (int)(prm.frame_off[u + 1] - f0);
-        const int t = (int)(g - f0);
-        float* out = prm.out + f0 * (3 * NC) + t;
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-            for (int c = 0; c < 10; ++c) out[(long long)(s * NC + 10 * q + c) * T] = half ? hi(acc[s][c]) : lo(acc[s][c]);
-    }
-}
-
 // ---- host launchers ----------------------------------------------------------------------------------------
 constexpr size_t kMaxSmem = 232448 - 64;  // 227 KB opt-in limit per CTA minus the static shared memory (TMEM base slot)
 
@@ -675,16 +553,6 @@ size_t extract_smem_bytes_for(int n_fft, int hop, int n_mel_entries) {
         case 1600: return extract_smem_bytes<32>(hop, n_mel_entries);
     }
     return 0;
-}
-
-cudaError_t launch_mfcc_dct(const MfccDctParams& prm, cudaStream_t stream) {
-    const long long blocks = (prm.total_frames + kDctFrames - 1) / kDctFrames;
-    if (blocks == 0) return cudaSuccess;
-    const size_t smem = kDctSmem;
-    cudaError_t e = cudaFuncSetAttribute(mfcc_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    mfcc_dct_kernel<<<(unsigned)blocks, kDctThreads, smem, stream>>>(prm);
-    return cudaGetLastError();
 }
 
 }  // namespace sept
