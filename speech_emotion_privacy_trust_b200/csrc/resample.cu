@@ -86,6 +86,9 @@ __host__ __device__ inline TileGeom resample_tile_geom(int orig, int n_groups, i
 // range with their own stage and their own named barrier: a third more resident warps for the same shared memory.
 __device__ __forceinline__ void half_barrier(int half) { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kTileThreads) : "memory"); }
 
+constexpr int kTileTapsFast = 43;                      // taps of a 4-phase group at 44.1 -> 16 kHz (the reference's MSP-Improv case)
+
+template <int TG>                                      // TG > 0: p.tg == TG, the tap loop is unrolled; 0: any tap count
 __global__ void __launch_bounds__(2 * kTileThreads) resample_tiled_kernel(const ResampleParams p) {
     const int half = threadIdx.x / kTileThreads, tid = threadIdx.x % kTileThreads;
     extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -144,10 +147,15 @@ __global__ void __launch_bounds__(2 * kTileThreads) resample_tiled_kernel(const 
         const float* src = src0 - shift;
         const int n_fill = n_stage + shift;
         if (s0 - shift >= 0 && s0 - shift + ((n_fill + 3) & ~3) <= n_in) {            // interior: no bounds tests, 16-byte loads
+            // asynchronous 16-byte copies (LDGSTS): the whole span is in flight at once and costs no registers -- one trip
+            // to memory per stage instead of one per unrolled group of loads; the fill latency is what this kernel waits for
             const float4* src4 = reinterpret_cast<const float4*>(src);
-            float4* dst4 = reinterpret_cast<float4*>(stage);
-#pragma unroll 4
-            for (int i = tid; i < (n_fill + 3) / 4; i += kTileThreads) dst4[i] = __ldg(src4 + i);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage);
+            const int n4 = (n_fill + 3) / 4;
+            for (int i = tid; i < n4; i += kTileThreads)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)i), "l"(src4 + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
             for (int i = tid; i < n_fill; i += kTileThreads) {
                 const long long idx = s0 - shift + i;
@@ -168,8 +176,7 @@ __global__ void __launch_bounds__(2 * kTileThreads) resample_tiled_kernel(const 
             pk2 acc2[4][2];
 #pragma unroll
             for (int r = 0; r < 4; ++r) { acc2[r][0] = splat(0.f); acc2[r][1] = splat(0.f); }
-#pragma unroll 4
-            for (int i = 0; i < p.tg; ++i) {
+            auto tap = [&](int i) {
                 const w4 wi = wp[i];
                 const float xv[4] = {x0[i], x1[i], x2[i], x3[i]};
 #pragma unroll
@@ -178,6 +185,13 @@ __global__ void __launch_bounds__(2 * kTileThreads) resample_tiled_kernel(const 
                     acc2[r][0] = fma2(wi.lo2, xs, acc2[r][0]);
                     acc2[r][1] = fma2(wi.hi2, xs, acc2[r][1]);
                 }
+            };
+            if constexpr (TG > 0) {                    // known tap count: straight-line code, the loads run ahead of their FMAs
+#pragma unroll
+                for (int i = 0; i < TG; ++i) tap(i);
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < p.tg; ++i) tap(i);
             }
             float acc[4][4];
 #pragma unroll
@@ -227,9 +241,10 @@ cudaError_t launch_resample(const ResampleParams& p, cudaStream_t stream) {
             long long blocks = (p.total_out + per_cta - 1) / per_cta;
             const long long resident = 148LL * (smem <= 72 * 1024 ? 3 : 2);   // CTAs of two independent halves
             if (blocks > resident) blocks = resident;              // persistent: the weight table is loaded once per CTA
-            cudaError_t e = cudaFuncSetAttribute(resample_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            auto kern = p.tg == kTileTapsFast ? resample_tiled_kernel<kTileTapsFast> : resample_tiled_kernel<0>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            resample_tiled_kernel<<<(unsigned)blocks, 2 * kTileThreads, smem, stream>>>(p);
+            kern<<<(unsigned)blocks, 2 * kTileThreads, smem, stream>>>(p);
             return cudaGetLastError();
         }
     }
