@@ -362,25 +362,50 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 #pragma unroll 1
         for (int stream = 0; stream < n_streams; ++stream) {
             const int deriv = (MODE == kModeMfccPower) ? stream : prm.deriv;
-            auto run_pass1 = [&](auto diff) {
+            // One copy of the 25-point transform for both kinds of stream, or one straight-line block per kind?  With the
+            // two instantiations the hot loop of the MFCC power kernel (both streams per item) held 27 KB of transform code
+            // and missed the instruction cache on a fifth of its fetches; sharing the transform made it 5 % faster and the
+            // n_fft 1600 kernel 3.8 % (smaller code), but costs the n_fft 800 dB kernel 1.8 % (one stream kind per launch:
+            // nothing to share, and the join after the loads keeps them from overlapping the first butterflies).
+            constexpr bool kSharedPass1 = !(R == 16 && MODE != kModeMfccPower);
+            if constexpr (kSharedPass1) {
+                if (cur.interior) {
+                    if (stream == 0) { cp_async_wait_all(); __syncwarp(); }
+                } else {
+                    __syncwarp();
+                    stage_item<G>(lane, cur.wav, cur.n, cur.t0, hop, deriv, stage);   // edge items: the stage already holds the stream
+                    __syncwarp();
+                }
+                SEPT_TICK(0);
+                const bool diff = cur.interior && deriv != 0;
                 if constexpr (FAST) {
                     WinRegs win;
                     win.load(taddr + TmemMap<R>::kWin);
-                    pass1<G, decltype(diff)::value>(lane, stage, hop, win, Y);
+                    pass1_shared<G>(lane, stage, hop, win, Y, diff);
                 } else {
-                    pass1<G, decltype(diff)::value>(lane, stage, hop, WinShared{win2}, Y);
+                    pass1_shared<G>(lane, stage, hop, WinShared{win2}, Y, diff);
                 }
-            };
-            if (cur.interior) {
-                if (stream == 0) { cp_async_wait_all(); __syncwarp(); }
-                SEPT_TICK(0);
-                if (deriv) run_pass1(std::true_type{});
-                else run_pass1(std::false_type{});
             } else {
-                __syncwarp();
-                stage_item<G>(lane, cur.wav, cur.n, cur.t0, hop, deriv, stage);
-                __syncwarp();
-                run_pass1(std::false_type{});
+                auto run_pass1 = [&](auto diff) {
+                    if constexpr (FAST) {
+                        WinRegs win;
+                        win.load(taddr + TmemMap<R>::kWin);
+                        pass1<G, decltype(diff)::value>(lane, stage, hop, win, Y);
+                    } else {
+                        pass1<G, decltype(diff)::value>(lane, stage, hop, WinShared{win2}, Y);
+                    }
+                };
+                if (cur.interior) {
+                    if (stream == 0) { cp_async_wait_all(); __syncwarp(); }
+                    SEPT_TICK(0);
+                    if (deriv) run_pass1(std::true_type{});
+                    else run_pass1(std::false_type{});
+                } else {
+                    __syncwarp();
+                    stage_item<G>(lane, cur.wav, cur.n, cur.t0, hop, deriv, stage);
+                    __syncwarp();
+                    run_pass1(std::false_type{});
+                }
             }
             SEPT_TICK(1);
             __syncwarp();                                        // stage is free, Y is complete

@@ -137,12 +137,11 @@ struct TwStrided {                                               // unfused pass
 // (audio_feature_extraction.py:20): the central difference (x[j+1] - x[j-1]) / 2 is taken on the fly from the
 // neighbouring sample pairs, the 1/2 riding on the window (exact: a power of two).
 template <class G, bool DIFF, class Win>
-SEPT_HD void pass1(int lane, const float* stage, int hop, const Win& win, pk2* Y) {
+SEPT_HD void pass1_load(int lane, const float* stage, int hop, const Win& win, pk2 (&re)[25], pk2 (&im)[25]) {
     constexpr int R = G::R;
     const int p = lane / R, n1 = lane % R;
     const f2* xa = reinterpret_cast<const f2*>(stage + G::LEAD + (2 * p) * hop);
     const f2* xb = reinterpret_cast<const f2*>(stage + G::LEAD + (2 * p + 1) * hop);
-    pk2 re[25], im[25];
 #pragma unroll
     for (int n2 = 0; n2 < 25; ++n2) {
         const int idx = Pfa<R>::in_index(n1, n2);
@@ -159,6 +158,12 @@ SEPT_HD void pass1(int lane, const float* stage, int hop, const Win& win, pk2* Y
             im[n2] = pk((ar.x - a.x) * hy, (br.x - b.x) * hy);
         }
     }
+}
+
+template <class G>
+SEPT_HD void pass1_transform_store(int lane, pk2 (&re)[25], pk2 (&im)[25], pk2* Y) {
+    constexpr int R = G::R;
+    const int p = lane / R, n1 = lane % R;
     Dft<25>::run(re, im);
     pk2* y = Y + p * G::YP + n1;
 #pragma unroll
@@ -166,6 +171,25 @@ SEPT_HD void pass1(int lane, const float* stage, int hop, const Win& win, pk2* Y
     // the fused pass reads row 0 as its own partner; a second copy in row 25 keeps that 16-byte read out of the bank
     // group of row 24 (rows 0 and 24 are 24 * RS * 8 bytes = a multiple of 128 apart)
     if (G::YROWS == 26) { y[25 * G::RS] = re[0]; y[25 * G::RS + R] = im[0]; }
+}
+
+// Two forms of the same pass.  pass1<G, DIFF>: loads and transform are one straight-line block per stream kind (the loads
+// overlap the first butterflies).  pass1_shared<G>: only the LOADS differ between the two streams (run-time, warp-uniform
+// `diff`), the 25-point transform behind them exists once -- so both MFCC streams of an item run through the same code.
+// Which one a kernel uses is decided by its instruction-cache footprint (extract.cu: kSharedPass1).
+template <class G, bool DIFF, class Win>
+SEPT_HD void pass1(int lane, const float* stage, int hop, const Win& win, pk2* Y) {
+    pk2 re[25], im[25];
+    pass1_load<G, DIFF>(lane, stage, hop, win, re, im);
+    pass1_transform_store<G>(lane, re, im, Y);
+}
+
+template <class G, class Win>
+SEPT_HD void pass1_shared(int lane, const float* stage, int hop, const Win& win, pk2* Y, bool diff) {
+    pk2 re[25], im[25];
+    if (!diff) pass1_load<G, false>(lane, stage, hop, win, re, im);
+    else pass1_load<G, true>(lane, stage, hop, win, re, im);
+    pass1_transform_store<G>(lane, re, im, Y);
 }
 
 // load one k2 row (R complex samples of a frame pair) with 16-byte loads of two neighbouring real / imaginary parts

@@ -38,8 +38,7 @@ int run(int hop, int n_mels, int deriv, const std::vector<float>& wav, const cha
         for (int lane = 0; lane < 32; ++lane)
             stage_item<G>(lane, wav.data(), n, t0, hop, interior ? 0 : deriv, stage.data());
         for (int lane = 0; lane < 32; ++lane) {
-            if (interior && deriv) pass1<G, true>(lane, stage.data(), hop, WinShared{win2}, Yp);
-            else pass1<G, false>(lane, stage.data(), hop, WinShared{win2}, Yp);
+            pass1_shared<G>(lane, stage.data(), hop, WinShared{win2}, Yp, interior && deriv);
         }
         const f2* tw2 = reinterpret_cast<const f2*>(tws.data());
         if constexpr (R <= 16) {
