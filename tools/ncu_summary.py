@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Condense an .ncu-rep (one profiled kernel launch) into the text summary kept under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/extract_r01.txt
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/extract_r01.txt [kernel-name regex, for reports with several kernels]
 """
 import csv
 import io
@@ -30,21 +30,22 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__share
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 
 
-def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+def page(rep, name, kernel=None):
+    cmd = ["ncu", "-i", rep, "--page", name, "--csv"] + (["--kernel-name", "regex:" + kernel] if kernel else [])
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
-def main(rep, dst):
+def main(rep, dst, kernel=None):
     lines = [f"ncu summary of {rep} (one launch, --set full --clock-control none)"]
-    raw = page(rep, "raw")
+    raw = page(rep, "raw", kernel)
     hdr, units, vals = raw[0], raw[1], raw[2]
     col = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
     lines.append(f"kernel: {col.get('Kernel Name', ('', '?'))[1]}")
     for k in KEYS:
         if k in col:
             lines.append(f"  {k} [{col[k][0]}] = {col[k][1]}")
-    src = page(rep, "source")[3:]
+    src = [r for r in page(rep, "source", kernel) if len(r) > 45 and r[0].startswith("0x")]       # SASS rows only
     tot = sum(int(r[4]) for r in src) or 1
     lines.append(f"\nSASS regions (100 instructions each): share of {tot} warp-stall samples, instructions executed, excess smem wavefronts, opcode mix")
     for b in range(0, len(src), 100):
@@ -66,4 +67,4 @@ def main(rep, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
