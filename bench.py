@@ -398,6 +398,9 @@ def secondary_metrics(args, dev, rank, world, batch=None, hours=None):
     other features the reference's extraction script computes per utterance (this rank's numbers, device resident)."""
     from benchmarks_train import cloak_kernel_bandwidth, eval_throughput, train_throughput
     out = train_throughput(dev, rank, world, steps=20, warmup=5)
+    if world > 1 and os.environ.get("SEPT_BENCH_TRAIN_AB") == "1":           # A/B of the gradient exchange in one run
+        ab = train_throughput(dev, rank, world, steps=20, warmup=5, overlap=True)
+        out["two_bucket_overlap_ab"] = {k: ab[k] for k in ("value", "ms_per_step", "allreduce")}
     if rank == 0:
         out["cloak_eval"] = eval_throughput(dev)
         out["cloak_kernels"] = cloak_kernel_bandwidth(dev)

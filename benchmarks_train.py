@@ -22,8 +22,14 @@ def build_model(dev, grl_lambda=0.1, seed=8):
     return cloak_models.two_d_cnn_lstm_syn_with_grl(mk("emotion"), mk("gender"), noise, grl_lambda).to(dev)
 
 
-def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_last=True, graphs=True):
+def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_last=True, graphs=True, overlap=None):
+    """overlap: reduce the adversary's recurrent / dense / head gradients on a side stream while backward runs through the
+    convolutions (two buckets); None = SEPT_TRAIN_OVERLAP (default off: measured 2.3 % SLOWER than one bucket on two GPUs,
+    5.37 vs 5.24 ms -- the forked NCCL kernel takes SMs from the convolution backward it overlaps)."""
+    import os
     import torch.distributed as dist
+    if overlap is None:
+        overlap = os.environ.get("SEPT_TRAIN_OVERLAP", "0") == "1"
     from speech_emotion_privacy_trust_b200 import losses, parallel, synth
     model = build_model(dev).train()
     if channels_last:
@@ -49,7 +55,7 @@ def train_throughput(dev, rank, world, steps=20, warmup=5, batch=32, channels_la
         from speech_emotion_privacy_trust_b200.train_step import GraphedTrainStep
         example = [hx[:batch].to(dev), hemo[:batch].to(dev), hgen[:batch].to(dev), w]
         # the layers nearest the loss (recurrent, dense, heads: 80 % of the gradient bytes) finish first in backward
-        early = [p for n, p in model.gender_model.named_parameters() if p.requires_grad and not n.startswith("conv.")]
+        early = [p for n, p in model.gender_model.named_parameters() if p.requires_grad and not n.startswith("conv.")] if overlap else []
         graphed = GraphedTrainStep(model, opt, loss_fn, example, data_parallel=world > 1, early_params=early)
 
     def step(i):
