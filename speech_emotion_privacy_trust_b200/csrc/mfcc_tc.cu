@@ -2,14 +2,15 @@
 // DCT-II (torchaudio/transforms/_transforms.py:714-717) as tcgen05.mma with the accumulators in tensor memory.
 //
 // Why tensor cores here and nowhere else on this path: the DCT is the one dense contraction of the extraction chain
-// ([frames x 128 bands] x [128 x 40], 49 % of an MFCC frame's flops) and ncu showed the FMA version (mfcc_dct_kernel,
-// extract.cu) with its FMA pipe 66 % busy at 184 us per audio-hour against 66 us of HBM time -- north_star's condition
-// for trying it ("only if ncu shows that small GEMM actually limits throughput").
-// Outcome (round 2, measured): parity green, 197 us per audio-hour -- no faster than the FMA kernel.  Stripped variants
-// (-DSEPT_TC_NO_MMA / NO_STORE / NO_CVT / NO_LOAD) put the cost where it is: the MMAs 11 us, the output stores 24 us, the
-// dB conversion 5 us, the global loads of the mel power 96 us, barriers + metadata + operand stores 63 us.  The phase is
-// bound by feeding the contraction, not by the contraction; the kernel is kept as an opt-in (SEPT_MFCC_DCT=tc) and as the
-// starting point for a TMA-fed version.
+// ([frames x 128 bands] x [128 x 40], 49 % of an MFCC frame's flops) and ncu showed round 1's FMA version with its FMA
+// pipe 66 % busy at 184 us per audio-hour against 66 us of HBM time -- north_star's condition for trying it ("only if ncu
+// shows that small GEMM actually limits throughput").
+// Outcome (round 2, measured): parity green, 197 us per audio-hour -- slower than the FMA kernel (mfcc_dct.cu: 125 us after
+// its rewrite).  Stripped variants (-DSEPT_TC_NO_MMA / NO_STORE / NO_CVT / NO_LOAD) put the cost where it is: the MMAs
+// 11 us, the output stores 24 us, the dB conversion 5 us, the global loads of the mel power 96 us, barriers + metadata +
+// operand stores 63 us.  The phase is bound by feeding the contraction, not by the contraction; the kernel is kept as an
+// opt-in (SEPT_MFCC_DCT=tc) and as the starting point for a version whose loads are asynchronous (a ring of raw tiles filled
+// by TMA / cp.async, converter warps, one MMA thread, epilogue warps) instead of one CTA-wide sequence of barriers.
 //
 // Precision: kind::tf32 multiplies 10-bit mantissas, far too coarse for the 1e-4 MFCC tolerance (dB values of +-100
 // against a basis of 0.09).  Both operands are split into a tf32-exact high part and the remainder,
