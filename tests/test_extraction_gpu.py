@@ -128,6 +128,29 @@ def test_gradient_stream_and_other_mel_counts(ex, golden_extraction):
         assert logmel_error(got.cpu().numpy().T, ref)[0] < TOL_DB
 
 
+def test_gradient_stream_every_fft_size(ex):
+    """np.gradient stream (deriv=True) through every kernel form: n_fft 800 keeps one straight-line pass 1 per stream kind,
+    n_fft 400 / 1600 share one transform behind a run-time switch of the loads (extract.cu: kSharedPass1); 128 bands take the
+    tensor-memory table path, 64 bands the shared-memory one.  Ragged batch: interior items difference the staged waveform
+    on the fly, edge items (reflection, utterance ends, one-sided differences) stage the gradient itself."""
+    from speech_emotion_privacy_trust_b200 import synth
+    rng = np.random.default_rng(91)
+    waves = [synth.speech_shaped(int(n), rng) for n in (16000, 801, 1700, 23456, 40000)]
+    batch = ex.RaggedAudio.from_list(waves)
+    for n_fft, hop in ((400, 200), (800, 160), (1600, 160)):
+        for n_mels in (128, 64):
+            fb = restate.melscale_fbanks_htk(n_fft // 2 + 1, n_mels)
+            got, lay = ex.logmel(batch, n_fft=n_fft, hop=hop, n_mels=n_mels, deriv=True)
+            fo = lay.frame_off_host
+            for u, w in enumerate(waves):
+                if len(w) <= n_fft // 2:
+                    continue
+                g = restate.waveform_gradient(w, 1.0).astype(np.float64)
+                ref = restate.amplitude_to_db_power((restate.power_spectrogram(g, n_fft, hop).T @ fb).T)
+                e_strong, e_all = logmel_error(got[fo[u]:fo[u + 1]].cpu().numpy().T, ref)
+                assert e_strong < TOL_DB and e_all < TOL_DB_FLOOR, (n_fft, n_mels, u, e_strong, e_all)
+
+
 def test_dropin_callables_keep_reference_types(golden_extraction):
     from speech_emotion_privacy_trust_b200 import dropin
     dropin.install()
