@@ -298,6 +298,22 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     for (int i = threadIdx.x; i < G::NC; i += blockDim.x) win2[i] = reinterpret_cast<const f2*>(prm.window)[i];
     uint32_t taddr = 0;                                           // this warp's quarter of the CTA's tensor memory
     __shared__ uint32_t tmem_base;
+    // ---- this CTA's contiguous item range.  kDynamicItems: its warps draw items from a shared counter instead of
+    // interleaving statically, so a warp that met edge items (reflection, utterance ends) does not hold the others up:
+    // MFCC 4.04 -> 3.92 ms, n_fft 1600 7.04 -> 6.94 ms per corpus; the n_fft 800 dB kernel LOSES 3 % with it and keeps
+    // the static interleave (A/B inside single runs, profiles/ab_dynamic_r02.log).  These kernels are sensitive to code
+    // layout at the +-2 % level (80 KB of straight-line code against the instruction cache): the range is computed early
+    // for the dynamic kernels and where it always was for the static one, which keeps the n_fft 800 kernel's SASS
+    // byte-identical to the measured one.
+    constexpr bool kDynamicItems = !(R == 16 && MODE != kModeMfccPower);
+    __shared__ int cta_next;
+    int n_items = 0, begin = 0, end = 0;
+    if constexpr (kDynamicItems) {
+        n_items = __ldg(prm.item_off + prm.n_utts);
+        begin = (int)((long long)n_items * blockIdx.x / gridDim.x);
+        end = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
+        if (threadIdx.x == 0) cta_next = begin;
+    }
     if constexpr (FAST) {
         if (warp == 0) tmem::alloc(&tmem_base, TmemMap<R>::kCols);
         tmem::fence_before_sync();
@@ -319,11 +335,19 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
     pk2* Y = reinterpret_cast<pk2*>(wbase + stage_floats * 4);
     pk2* P = Y;
 
-    // ---- this CTA's contiguous item range; warps interleave inside it --------------------------------------
-    const int n_items = __ldg(prm.item_off + prm.n_utts);
-    const int begin = (int)((long long)n_items * blockIdx.x / gridDim.x);
-    const int end = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
-    int item = begin + warp;
+    if constexpr (!kDynamicItems) {
+        n_items = __ldg(prm.item_off + prm.n_utts);
+        begin = (int)((long long)n_items * blockIdx.x / gridDim.x);
+        end = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
+    }
+    auto grab = [&]() {                                           // next item of the CTA (>= end: none left); ascending per warp
+        int v = 0;
+        if (lane == 0) v = atomicAdd(&cta_next, 1);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    int item;
+    if constexpr (kDynamicItems) item = grab();
+    else item = begin + warp;
     const bool active = item < end;                               // idle warps still reach the barrier at the end
     int u = active ? find_utt(prm.item_off, prm.n_utts, item) : 0;
     int u_first = __ldg(prm.item_off + u), u_last = __ldg(prm.item_off + u + 1);
@@ -358,7 +382,8 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
 #ifdef SEPT_PHASE_CLOCKS
     long long tick_last = clock64();
 #endif
-    for (; item < end; item += kExtractWarps) {
+    for (; item < end; item = kDynamicItems ? item : item + kExtractWarps) {     // dynamic: advanced at the end of the body
+        int item_next = end;
 #pragma unroll 1
         for (int stream = 0; stream < n_streams; ++stream) {
             const int deriv = (MODE == kModeMfccPower) ? stream : prm.deriv;
@@ -412,7 +437,15 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
             SEPT_TICK(2);
 
             ItemRef nxt = cur;
-            if (stream == n_streams - 1 && item + kExtractWarps < end) {
+            if constexpr (kDynamicItems) {
+                if (stream == n_streams - 1) {
+                    item_next = grab();
+                    if (item_next < end) {
+                        nxt = locate(item_next);
+                        if (nxt.interior) prefetch(nxt);         // overlaps pass 2, split and mel of this item
+                    }
+                }
+            } else if (stream == n_streams - 1 && item + kExtractWarps < end) {
                 nxt = locate(item + kExtractWarps);
                 if (nxt.interior) prefetch(nxt);                 // overlaps pass 2, split and mel of this item
             }
@@ -480,6 +513,7 @@ __global__ void __launch_bounds__(ExtractWarps<R>::value * 32, 1) extract_kernel
             SEPT_TICK(9);
             if (stream == n_streams - 1) cur = nxt;
         }
+        if constexpr (kDynamicItems) item = item_next;
     }
     if constexpr (FAST) {
         tmem::fence_before_sync();
